@@ -1,0 +1,138 @@
+"""CPU tests: the oracle (oracle/decode_oracle.c via oracle/oracle.py) against the golden vectors produced by the
+reference's own Python code (oracle/make_golden.py).  This is what pins the oracle (task section 3)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+@pytest.mark.parametrize("fmt", ["gptq", "awq"])
+def test_unpack_groupwise_matches_reference_loader(golden_dir, fmt):
+    g = _load(golden_dir, f"quant_unpack_{fmt}.npz")
+    qp, zs, sc = orc.unpack_groupwise_int4(g["qweight"], g["qzeros"], g["scales"], int(g["group"]), fmt == "gptq")
+    assert np.array_equal(qp, g["q_packed"])                      # bit-exact nibbles
+    assert np.array_equal(zs.view(np.uint16), g["zeros_x_scales"].view(np.uint16))  # bit-exact fp16
+    assert np.array_equal(sc.view(np.uint16), g["scales_out"].view(np.uint16))
+
+
+def test_int8_per_column_quantiser_matches_reference(golden_dir):
+    g = _load(golden_dir, "quant_int8.npz")
+    q, s = orc.quantize_int8_per_col(g["weight"])
+    assert np.array_equal(q, g["q"])
+    assert np.array_equal(s, g["scale"].astype(np.float32))
+
+
+@pytest.mark.parametrize("name", ["attn_p16_gqa4", "attn_p64_gqa8", "attn_p32_mha"])
+def test_paged_decode_attention_matches_reference_oracle(golden_dir, name):
+    g = _load(golden_dir, f"{name}.npz")
+    page_list = orc.convert_block_table(g["block_ids"])
+    out = orc.paged_decode_attn(g["q"].view(np.uint16), g["kv_pool"].view(np.uint16), page_list,
+                                g["sequence_lengths"], int(g["head_num"]), int(g["kv_head_num"]),
+                                int(g["head_dim"]), int(g["tokens_per_block"]))
+    got = orc.from_bits(out, False)
+    # reference tolerance: rtol = atol = 1e-2 (base_attention_test.py:147-148)
+    np.testing.assert_allclose(got, g["expect"], rtol=1e-2, atol=1e-2)
+    # and the float64 numpy restatement agrees much tighter than that
+    ref64 = orc.paged_decode_attn_np(g["q"].astype(np.float64), g["kv_pool"].astype(np.float64), g["block_ids"],
+                                     g["sequence_lengths"], int(g["tokens_per_block"]))
+    np.testing.assert_allclose(got, ref64, rtol=2e-3, atol=2e-3)
+
+
+def test_indexing_matches_reference_expected_values(golden_dir):
+    g = _load(golden_dir, "indexing.npz")
+    got = orc.convert_block_table(g["block_id"])
+    assert np.array_equal(got[:, 0], g["kv_offset"])
+    assert np.array_equal(orc.convert_block_table_np(g["block_id"]), got)
+    for tag in "abcd":
+        lens, T = g[f"plan_{tag}_lens"], int(g[f"plan_{tag}_T"])
+        nb = [-(-int(L) // T) for L in lens]
+        M = max(nb)
+        block_ids = np.zeros((len(lens), M), np.int32)
+        off = 0
+        for b, n in enumerate(nb):
+            block_ids[b, :n] = np.arange(off, off + n)
+            off += n
+        plan = orc.paged_attn_plan(lens - 1, block_ids, T)     # engine passes len-1
+        assert np.array_equal(plan["page_indptr"], g[f"plan_{tag}_indptr"])
+        assert np.array_equal(plan["page_indice"], g[f"plan_{tag}_indices"])
+        assert np.array_equal(plan["last_page_len"], g[f"plan_{tag}_last"])
+        assert np.array_equal(plan["positions"], lens - 1)
+        assert np.array_equal(plan["batch_indice"], np.arange(len(lens)))
+
+
+@pytest.mark.parametrize("fmt", ["f16", "int8", "int4"])
+def test_dequant_gemm_c_vs_numpy(fmt):
+    rng = np.random.default_rng(7)
+    B, K, N, group = 5, 256, 96, 128
+    x = (rng.standard_normal((B, K))).astype(np.float16)
+    if fmt == "f16":
+        w = (rng.standard_normal((K, N)) * 0.05).astype(np.float16)
+        wd = orc.dequant_np("f16", w.astype(np.float32))
+        y = orc.dequant_gemm(x.view(np.uint16), "f16", w.view(np.uint16))
+    elif fmt == "int8":
+        q = rng.integers(-128, 128, (K, N)).astype(np.int8)
+        s = (np.abs(rng.standard_normal(N)) * 0.01 + 1e-3).astype(np.float16)
+        wd = orc.dequant_np("int8", q, s)
+        y = orc.dequant_gemm(x.view(np.uint16), "int8", q, scales=s)
+    else:
+        qp = rng.integers(0, 256, (K, N // 2)).astype(np.uint8)
+        s = (np.abs(rng.standard_normal((K // group, N))) * 0.01 + 1e-3).astype(np.float16)
+        z = rng.integers(0, 16, (K // group, N))
+        zs = ((8 - z).astype(np.float16) * s).astype(np.float16)
+        wd = orc.dequant_np("int4", qp, s, zs, group)
+        y = orc.dequant_gemm(x.view(np.uint16), "int4", qp, scales=s, zeros_x_scales=zs, group=group)
+        yf = orc.dequant_gemm(x.view(np.uint16), "int4", qp, scales=s, zeros_x_scales=zs, group=group, fast=True)
+        np.testing.assert_allclose(orc.from_bits(yf, False), orc.from_bits(y, False), rtol=2e-3, atol=2e-3)
+    ref = (x.astype(np.float64) @ wd.astype(np.float64)).astype(np.float16).astype(np.float32)
+    np.testing.assert_allclose(orc.from_bits(y, False), ref, rtol=1e-3, atol=1e-3)
+
+
+def test_glue_ops_against_numpy():
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((3, 64)).astype(np.float16)
+    r = rng.standard_normal((3, 64)).astype(np.float16)
+    gmm = rng.standard_normal(64).astype(np.float16)
+    y, res = orc.add_rmsnorm(x.view(np.uint16), r.view(np.uint16), gmm.view(np.uint16), 1e-6)
+    rr = (x.astype(np.float32) + r.astype(np.float32)).astype(np.float16)
+    assert np.array_equal(res.view(np.float16), rr)
+    rf = rr.astype(np.float32)
+    exp = rf / np.sqrt((rf * rf).mean(-1, keepdims=True) + 1e-6) * gmm.astype(np.float32)
+    np.testing.assert_allclose(orc.from_bits(y, False), exp, rtol=2e-3, atol=2e-3)
+    gu = rng.standard_normal((3, 32)).astype(np.float16)
+    s = orc.silu_and_mul(gu.view(np.uint16))
+    gf, uf = gu[:, :16].astype(np.float32), gu[:, 16:].astype(np.float32)
+    np.testing.assert_allclose(orc.from_bits(s, False), gf / (1 + np.exp(-gf)) * uf, rtol=2e-3, atol=2e-3)
+    lg = rng.standard_normal((4, 1000)).astype(np.float32)
+    lg[2, 10] = lg[2, 500] = 99.0
+    assert np.array_equal(orc.argmax(lg), lg.argmax(-1).astype(np.int32))
+
+
+def test_rope_append_roundtrip_properties():
+    rng = np.random.default_rng(5)
+    B, Hq, Hkv, D, T, M = 2, 4, 2, 128, 16, 3
+    qkv = rng.standard_normal((B, (Hq + 2 * Hkv) * D)).astype(np.float16)
+    pool = np.zeros((1 + B * M, 2, Hkv, T, D), np.float16)
+    block_ids = (np.arange(B * M, dtype=np.int32) + 1).reshape(B, M)
+    pl = orc.convert_block_table(block_ids)
+    seq = np.array([0, 37], np.int32)
+    q, pool2 = orc.rope_append(qkv.view(np.uint16), pool.view(np.uint16), pl, seq, Hq, Hkv, D, T, 500000.0)
+    q = q.view(np.float16).reshape(B, Hq, D)
+    pool2 = pool2.view(np.float16).reshape(pool.shape)
+    # position 0 -> identity rotation
+    np.testing.assert_array_equal(q[0], qkv[0, : Hq * D].reshape(Hq, D))
+    # rotation preserves the norm of each (i, i+D/2) pair
+    src = qkv[1, : Hq * D].reshape(Hq, D).astype(np.float32)
+    n0 = src[:, :64] ** 2 + src[:, 64:] ** 2
+    n1 = q[1, :, :64].astype(np.float32) ** 2 + q[1, :, 64:].astype(np.float32) ** 2
+    np.testing.assert_allclose(n1, n0, rtol=5e-3, atol=5e-3)
+    # V copied verbatim to page block_ids[1][37//16], slot 37%16
+    v = qkv[1, (Hq + Hkv) * D:].reshape(Hkv, D)
+    np.testing.assert_array_equal(pool2[block_ids[1, 2], 1, :, 37 % 16, :], v)
+    # nothing else written
+    assert np.count_nonzero(pool2) <= 2 * 2 * Hkv * D
