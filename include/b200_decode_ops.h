@@ -1,0 +1,139 @@
+/*
+ * b200_decode_ops.h -- C ABI of libb200_decode.so: the B200-native (sm_100a) decode hot path of rtp-llm.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain device pointers, sizes and a cudaStream_t (passed as
+ * void*), returns 0 on success or a negative B200_E* code (message via b200_last_error()), never synchronises the
+ * stream, never allocates device memory and is CUDA-graph capturable.  No torch types cross this boundary.
+ *
+ * Each function names the reference interface it replaces (paths relative to the rtp-llm repo root).
+ * INTEGRATION.md shows the reference-side binding for each.
+ */
+#ifndef B200_DECODE_OPS_H
+#define B200_DECODE_OPS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_EINVAL (-1)      /* bad argument (shape, alignment, unsupported configuration) */
+#define B200_ECUDA (-2)       /* a CUDA runtime / driver call failed */
+#define B200_EUNSUPPORTED (-3) /* not an sm_100 device, or feature outside the built scope */
+
+/* weight formats of b200_wo_gemm */
+#define B200_FMT_F16 0   /* W stored [N][K] (K contiguous), element type = activation type */
+#define B200_FMT_INT8 1  /* per-column symmetric INT8 (device_impl.py:183-222), packed by b200_pack_w8 */
+#define B200_FMT_INT4 2  /* GPTQ/AWQ group-128 INT4 (device_impl.py:242-300), packed by b200_pack_w4 */
+
+/* flags of b200_wo_gemm */
+#define B200_GEMM_PDL 1  /* launch with programmatic dependent launch (weights prefetched before the upstream grid ends) */
+
+/* Last error message of the calling thread ("" if none). */
+const char* b200_last_error(void);
+
+/* 0 if device `device` is sm_100 (B200) and the library's kernels can run there, else B200_EUNSUPPORTED. */
+int b200_device_check(int device);
+
+/* Number of kernels this library has launched since load (all threads); used by bench.py for "gpu_launches". */
+uint64_t b200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------ indexing */
+
+/* Replaces invokeConvertOffsetToBlockArrayData
+ *   rtp_llm/models_py/bindings/common/kernels/kv_cache_kernels.cu:66-80 (kernel :49-63).
+ * block_ids [batch][max_blocks] int32 -> page_list [batch][1][2][max_blocks] int32, K page = 2*id, V page = 2*id+1. */
+int b200_convert_block_table(int32_t* page_list, const int32_t* block_ids, int batch, int max_blocks, void* stream);
+
+/* Replaces invokeMhaPagedAttnPlan  rtp_llm/models_py/bindings/cuda/kernels/mha_paged_attn_plan.cu:100-180 (kernel :16-97).
+ * prefix_lengths == NULL selects decode mode (one token per sequence, seq_len = sequence_lengths[b]+1).
+ * block_ids may be NULL (page_indice untouched). batch <= 1024. */
+int b200_paged_attn_plan(const int32_t* input_lengths, const int32_t* sequence_lengths, const int32_t* prefix_lengths,
+                         const int32_t* block_ids, int batch, int max_blocks, int tokens_per_block,
+                         int32_t* paged_kv_last_page_len, int32_t* decode_page_indptr, int32_t* page_indice,
+                         int32_t* batch_indice, int32_t* positions, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ attention */
+
+/* Bytes of scratch b200_paged_decode_attn needs for this problem size. The buffer must be zero-filled ONCE after
+ * allocation (cudaMemset); the kernels leave it zeroed where it matters (semaphores self-reset). */
+size_t b200_paged_decode_attn_workspace_bytes(size_t batch, size_t head_num, size_t kv_head_num, size_t max_seq_len);
+
+/* Replaces runXqa  rtp_llm/models_py/bindings/cuda/ops/CudaXqa.h:65-84 (called from XQAAttnOp::forward,
+ * rtp_llm/models_py/bindings/cuda/XQAAttnOp.cc:119-156) and the flashinfer trtllm-gen call at
+ * rtp_llm/models_py/modules/factory/attention/cuda_impl/trtllm_gen.py:531-545.
+ *   q            [batch][head_num][head_dim]                        fp16 / bf16
+ *   out          [batch][head_num*head_dim]                         same type
+ *   kv_pool      layer cache [pages][2][kv_head_num][page_size][head_dim] (OpDefs.h:201-202), addressed as a pool of
+ *                2*pages pages of [kv_head_num][page_size][head_dim]
+ *   page_list    [batch][1][2][max_blocks_per_seq] int32 from b200_convert_block_table
+ *   sequence_lengths [batch] tokens ALREADY in the cache (device-accessible; pinned host memory works, as in the
+ *                reference); attention covers positions 0..sequence_lengths[b] inclusive
+ *   max_seq_len  host upper bound of sequence_lengths[b]+1 (sizes the sequence split; as XQAAttnOp.cc:149)
+ *   softmax scale = q_scale * head_dim^-1/2.
+ * Supported: head_dim 128, head_num/kv_head_num in 1..16, page_size in {16,32,64,128}. */
+int b200_paged_decode_attn(const void* q, int is_bf16, void* out, size_t head_num, size_t kv_head_num, size_t head_dim,
+                           size_t batch, size_t max_blocks_per_seq, size_t max_seq_len, size_t page_size,
+                           const void* kv_pool, const int32_t* page_list, const uint32_t* sequence_lengths,
+                           float q_scale, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ weight-only GEMM */
+
+/* Load-time weight re-layout.  Replace CudaImpl.preprocess_weights_for_mixed_gemm (rtp_llm/device/device_impl.py:392-479):
+ * instead of the FT sm80 interleave, weights become per-(128 features x 128 k) blobs that one TMA bulk copy stages.
+ * Inputs are the loader's UN-permuted tensors (device pointers):
+ *   b200_pack_w4: q_packed uint8 [K][N/2] (low nibble = even column, two's complement q_s = q_u - 8, device_impl.py:204-209),
+ *                 scales, zeros_x_scales [K/128][N] 16-bit in the ACTIVATION type (fp16 or bf16)
+ *   b200_pack_w8: q int8 [K][N] (device_impl.py:183-202); the per-column scale stays a separate [N] tensor
+ * K % 128 == 0; N % 2 == 0 (int4). Output size: b200_wo_gemm_packed_bytes(fmt, K, N). */
+size_t b200_wo_gemm_packed_bytes(int fmt, int K, int N);
+int b200_pack_w4(const uint8_t* q_packed, const void* scales, const void* zeros_x_scales, int K, int N, int group,
+                 void* blob, void* stream);
+int b200_pack_w8(const int8_t* q, int K, int N, void* blob, void* stream);
+
+/* Scratch for split-K partials + semaphores; zero-fill once after allocation. */
+size_t b200_wo_gemm_workspace_bytes(int max_batch, int N, int K);
+
+/* Y[B][N] = X[B][K] . W' (+ bias).  The compute behind LinearBase.forward
+ * (rtp_llm/models_py/modules/factory/linear/linear_base.py:81; call sites modules/hybrid/causal_attention.py:83,90,
+ * dense_mlp.py:99,103; lm_head cpp/models/PyWrappedModel.cc:1041-1046) for weight-only INT4/INT8 and FP16 weights.
+ *   w         B200_FMT_INT4/INT8: blob from b200_pack_w4/8; B200_FMT_F16: W [N][K] (K contiguous)
+ *   col_scale INT8 only: [N] per-column scale in the activation type
+ *   bias      optional [N]
+ * B <= 128, K % 128 == 0, x / y / w 16-byte aligned. */
+int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const void* w, const void* col_scale,
+                 const void* bias, void* y, void* workspace, size_t workspace_bytes, int flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ glue ops */
+
+/* fused_add_rmsnorm / rmsnorm (rtp_llm/models_py/bindings/cuda/RegisterBaseBindings.hpp:45-160).
+ * residual may be NULL; otherwise residual += x (in place) and y = rmsnorm(residual) * gamma. hidden % 8 == 0. */
+int b200_add_rmsnorm(const void* x, void* residual, const void* gamma, void* y, int is_bf16, int rows, int hidden,
+                     float eps, void* stream);
+/* silu_and_mul: y[r][c] = silu(gate_up[r][c]) * gate_up[r][inter + c]. */
+int b200_silu_and_mul(const void* gate_up, void* y, int is_bf16, int rows, int inter, void* stream);
+/* FusedRopeKVCacheDecodeOp.forward (rtp_llm/ops/fused_rope_kvcache_op.py:202-246), RopeStyle::Base, NeoX pairing:
+ * rotates q and k of qkv [B][(Hq+2Hkv)*D] at position sequence_lengths[b], writes q to q_out [B][Hq*D] and K,V of the
+ * new token into the paged cache. */
+int b200_rope_append(const void* qkv, void* q_out, void* kv_pool, const int32_t* page_list,
+                     const int32_t* sequence_lengths, int is_bf16, int batch, int head_num, int kv_head_num,
+                     int head_dim, int max_blocks_per_seq, int page_size, float rope_base, void* stream);
+/* embedding gather out[b] = table[ids[b]] (rtp_ops.embedding). */
+int b200_embedding(const int32_t* ids, const void* table, void* out, int is_bf16, int rows, int hidden, void* stream);
+/* greedy sampling: out[r] = argmax(logits[r]) (lowest index on ties; CudaSampleOp.cc:330,453). dtype: 0 fp16, 1 bf16, 2 fp32 */
+int b200_argmax(const void* logits, int dtype, int rows, int vocab, int32_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ GPU-side checkers */
+/* Deliberately naive CUDA-core kernels over the UN-permuted reference tensors; used by tests only. */
+int b200_ref_paged_decode_attn(const void* q, int is_bf16, void* out, int head_num, int kv_head_num, int head_dim,
+                               int batch, int max_blocks_per_seq, int page_size, const void* kv_pool,
+                               const int32_t* page_list, const int32_t* sequence_lengths, float q_scale, void* stream);
+int b200_ref_dequant_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const void* w, const void* scales,
+                          const void* zeros_x_scales, int group, const void* bias, void* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_DECODE_OPS_H */

@@ -1,0 +1,64 @@
+"""ctypes binding of libb200_decode.so (include/b200_decode_ops.h). Fails loudly: there is no CPU or PyTorch fallback."""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_size_t, c_uint64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200_decode.so")
+
+B200_FMT_F16, B200_FMT_INT8, B200_FMT_INT4 = 0, 1, 2
+B200_GEMM_PDL = 1
+
+# name -> (restype, argtypes): mirrors include/b200_decode_ops.h one to one (tests check every symbol resolves)
+SIGNATURES = {
+    "b200_last_error": (c_char_p, []),
+    "b200_device_check": (c_int, [c_int]),
+    "b200_launch_count": (c_uint64, []),
+    "b200_convert_block_table": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "b200_paged_attn_plan": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p] * 5 + [c_void_p]),
+    "b200_paged_decode_attn_workspace_bytes": (c_size_t, [c_size_t] * 4),
+    "b200_paged_decode_attn": (c_int, [c_void_p, c_int, c_void_p] + [c_size_t] * 7 + [c_void_p, c_void_p, c_void_p,
+                                       c_float, c_void_p, c_size_t, c_void_p]),
+    "b200_wo_gemm_packed_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "b200_pack_w4": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b200_pack_w8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "b200_wo_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "b200_wo_gemm": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_size_t, c_int, c_void_p]),
+    "b200_add_rmsnorm": (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_float, c_void_p]),
+    "b200_silu_and_mul": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b200_rope_append": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_float, c_void_p]),
+    "b200_embedding": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b200_argmax": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b200_ref_paged_decode_attn": (c_int, [c_void_p, c_int, c_void_p] + [c_int] * 6 + [c_void_p] * 3 + [c_float, c_void_p]),
+    "b200_ref_dequant_gemm": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_int] + [c_void_p] * 3 + [c_int, c_void_p,
+                                      c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+class B200Error(RuntimeError):
+    """Raised for every non-zero status of the C ABI (mirrors RTP_LLM_CHECK_WITH_INFO -> RuntimeError in the reference,
+    rtp_llm/cpp/utils/AssertUtils.h:18-27)."""
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200Error(f"{LIB_PATH} is missing: run `python -m rtp_llm_b200.build` (nvcc, sm_100a). "
+                            "There is no fallback path.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the header and the library ever diverge
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().b200_last_error().decode()
+        raise B200Error(f"{what} failed (status {status}): {msg}")

@@ -1,0 +1,334 @@
+// Small HBM-bound kernels either side of the two hot kernels: page-table indexing, the glue ops of a decode layer
+// (SURVEY.md section 8f rows 1-3), greedy sampling, and deliberately naive CUDA-core reference kernels used only by the
+// GPU parity tests at sizes the CPU oracle cannot reach.
+#pragma once
+#include "ptx.cuh"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------- indexing
+// block table [B][M] -> page list [B][2][M] (K = 2*id, V = 2*id+1); bit-exact restatement of the behaviour of
+// /root/reference/rtp_llm/models_py/bindings/common/kernels/kv_cache_kernels.cu:49-63.
+__global__ void convert_block_table_kernel(int32_t* __restrict__ page_list, const int32_t* __restrict__ block_ids,
+                                           int batch, int max_blocks) {
+    const int total = batch * max_blocks;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int b = idx / max_blocks, j = idx - b * max_blocks;
+        const int32_t id = block_ids[idx];
+        page_list[(size_t)(2 * b) * max_blocks + j] = id * 2;
+        page_list[(size_t)(2 * b + 1) * max_blocks + j] = id * 2 + 1;
+    }
+}
+
+// decode-mode flashinfer plan metadata (mha_paged_attn_plan.cu:28-97, decode branch + prefill branch).
+// One CTA; a warp-shuffle scan replaces the reference's thread-0 serial scan.
+__global__ void paged_attn_plan_kernel(const int32_t* __restrict__ input_lengths,
+                                       const int32_t* __restrict__ sequence_lengths,
+                                       const int32_t* __restrict__ prefix_lengths,
+                                       const int32_t* __restrict__ block_ids, int batch, int max_blocks,
+                                       int tokens_per_block, int32_t* __restrict__ last_page_len,
+                                       int32_t* __restrict__ page_indptr, int32_t* __restrict__ page_indice,
+                                       int32_t* __restrict__ batch_indice, int32_t* __restrict__ positions) {
+    __shared__ int32_t s_wp[32], s_wt[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int input_len = 0, prefix_len = 0, seq_len = 0, pages = 0;
+    if (tid < batch) {
+        if (prefix_lengths) {
+            input_len = input_lengths[tid];
+            prefix_len = prefix_lengths[tid];
+            seq_len = input_len + prefix_len;
+        } else {
+            input_len = 1;
+            seq_len = sequence_lengths[tid] + 1;
+        }
+        pages = (seq_len + tokens_per_block - 1) / tokens_per_block;
+        last_page_len[tid] = (seq_len - 1) % tokens_per_block + 1;
+    }
+    // inclusive warp scans, then scan of warp totals
+    int ip = pages, itk = input_len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int vp = __shfl_up_sync(0xffffffffu, ip, o), vt = __shfl_up_sync(0xffffffffu, itk, o);
+        if (lane >= o) {
+            ip += vp;
+            itk += vt;
+        }
+    }
+    if (lane == 31) {
+        s_wp[wid] = ip;
+        s_wt[wid] = itk;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        int wp = s_wp[lane], wt = s_wt[lane];
+        const int nw = (blockDim.x + 31) >> 5;
+        if (lane >= nw) wp = wt = 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int vp = __shfl_up_sync(0xffffffffu, wp, o), vt = __shfl_up_sync(0xffffffffu, wt, o);
+            if (lane >= o) {
+                wp += vp;
+                wt += vt;
+            }
+        }
+        s_wp[lane] = wp;
+        s_wt[lane] = wt;
+    }
+    __syncthreads();
+    const int pbase = (wid ? s_wp[wid - 1] : 0), tbase = (wid ? s_wt[wid - 1] : 0);
+    const int p_end = pbase + ip, t_end = tbase + itk;
+    if (tid == 0) page_indptr[0] = 0;
+    if (tid < batch) {
+        page_indptr[tid + 1] = p_end;
+        const int p_start = p_end - pages, t_start = t_end - input_len;
+        if (prefix_lengths) {
+            for (int j = 0; j < input_len; ++j) {
+                batch_indice[t_start + j] = tid;
+                positions[t_start + j] = j + prefix_len;
+            }
+        } else {
+            batch_indice[t_start] = tid;
+            positions[t_start] = sequence_lengths[tid];
+        }
+        if (block_ids)
+            for (int j = 0; j < pages; ++j) page_indice[p_start + j] = block_ids[(size_t)tid * max_blocks + j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- glue ops
+template <typename T>
+__device__ __forceinline__ float2 unpack2(uint32_t v);
+template <>
+__device__ __forceinline__ float2 unpack2<__half>(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
+template <>
+__device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t v) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
+}
+
+// y = rmsnorm(x (+ residual)) * gamma; residual (if given) is updated in place with x + residual (rounded to T).
+// One CTA per row, 16-byte vector loads, hidden % 8 == 0.  (fused_add_rmsnorm / rmsnorm of RegisterBaseBindings.hpp:45-160)
+template <typename T>
+__global__ void add_rmsnorm_kernel(const T* __restrict__ x, T* __restrict__ residual, const T* __restrict__ gamma,
+                                   T* __restrict__ y, int hidden, float eps) {
+    extern __shared__ float s_row[];  // hidden floats
+    __shared__ float s_red[32];
+    const int row = blockIdx.x;
+    const uint4* xv = reinterpret_cast<const uint4*>(x + (size_t)row * hidden);
+    uint4* rv = residual ? reinterpret_cast<uint4*>(residual + (size_t)row * hidden) : nullptr;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < hidden / 8; i += blockDim.x) {
+        uint4 a = xv[i];
+        uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+        if (rv) {
+            uint4 r = rv[i];
+            uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 fa = unpack2<T>(aw[j]), fr = unpack2<T>(rw[j]);
+                aw[j] = pack2<T>(fa.x + fr.x, fa.y + fr.y);
+            }
+            rv[i] = make_uint4(aw[0], aw[1], aw[2], aw[3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 f = unpack2<T>(aw[j]);
+            s_row[i * 8 + j * 2] = f.x;
+            s_row[i * 8 + j * 2 + 1] = f.y;
+            ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) s_red[0] = rsqrtf(v / hidden + eps);
+    }
+    __syncthreads();
+    const float inv = s_red[0];
+    const uint4* gv = reinterpret_cast<const uint4*>(gamma);
+    uint4* yv = reinterpret_cast<uint4*>(y + (size_t)row * hidden);
+    for (int i = threadIdx.x; i < hidden / 8; i += blockDim.x) {
+        uint4 g = gv[i];
+        uint32_t gw[4] = {g.x, g.y, g.z, g.w}, ow[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 fg = unpack2<T>(gw[j]);
+            ow[j] = pack2<T>(s_row[i * 8 + j * 2] * inv * fg.x, s_row[i * 8 + j * 2 + 1] * inv * fg.y);
+        }
+        yv[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+}
+
+// y[r][c] = silu(gate_up[r][c]) * gate_up[r][inter + c]   (activation_kernels.cu silu_and_mul semantics)
+template <typename T>
+__global__ void silu_and_mul_kernel(const T* __restrict__ gate_up, T* __restrict__ y, int rows, int inter) {
+    const size_t total = (size_t)rows * inter / 2;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = idx / (inter / 2), c2 = idx % (inter / 2);
+        const uint32_t g = reinterpret_cast<const uint32_t*>(gate_up + r * 2 * inter)[c2];
+        const uint32_t u = reinterpret_cast<const uint32_t*>(gate_up + r * 2 * inter + inter)[c2];
+        float2 fg = unpack2<T>(g), fu = unpack2<T>(u);
+        float s0 = fg.x / (1.f + __expf(-fg.x)), s1 = fg.y / (1.f + __expf(-fg.y));
+        reinterpret_cast<uint32_t*>(y + r * inter)[c2] = pack2<T>(s0 * fu.x, s1 * fu.y);
+    }
+}
+
+// Decode RoPE (NeoX pairing, RopeStyle::Base, angle = pos * base^(-2i/dim)) + K,V append into the paged cache.
+// Contract: SURVEY.md appendix C; call site /root/reference/rtp_llm/ops/fused_rope_kvcache_op.py:202-246.
+// grid (B, Hq + 2*Hkv), D/2 threads.
+template <typename T>
+__global__ void rope_append_kernel(const T* __restrict__ qkv, T* __restrict__ q_out, T* __restrict__ kv_pool,
+                                   const int32_t* __restrict__ page_list, const int32_t* __restrict__ seq_lens,
+                                   int head_num, int kv_head_num, int head_dim, int max_blocks, int tokens_per_block,
+                                   float log2_base) {
+    const int b = blockIdx.x, h = blockIdx.y, i = threadIdx.x, half = head_dim / 2;
+    const int pos = seq_lens[b];
+    const T* src = qkv + ((size_t)b * (head_num + 2 * kv_head_num) + h) * head_dim;
+    const size_t page_elems = (size_t)kv_head_num * tokens_per_block * head_dim;
+    T* dst;
+    bool rotate = true;
+    if (h < head_num) {
+        dst = q_out + ((size_t)b * head_num + h) * head_dim;
+    } else {
+        const bool is_v = h >= head_num + kv_head_num;
+        const int kvh = is_v ? h - head_num - kv_head_num : h - head_num;
+        const int32_t page = page_list[((size_t)b * 2 + (is_v ? 1 : 0)) * max_blocks + pos / tokens_per_block];
+        dst = kv_pool + (size_t)page * page_elems + ((size_t)kvh * tokens_per_block + pos % tokens_per_block) * head_dim;
+        rotate = !is_v;
+    }
+    const float x0 = to_f32<T>(src[i]), x1 = to_f32<T>(src[i + half]);
+    if (rotate) {
+        const float inv_freq = exp2f(-2.0f * (float)i / (float)head_dim * log2_base);
+        float sn, cs;
+        sincosf((float)pos * inv_freq, &sn, &cs);
+        dst[i] = from_f32<T>(x0 * cs - x1 * sn);
+        dst[i + half] = from_f32<T>(x1 * cs + x0 * sn);
+    } else {
+        dst[i] = src[i];
+        dst[i + half] = src[i + half];
+    }
+}
+
+// token embedding gather: out[b][:] = table[ids[b]][:]
+template <typename T>
+__global__ void embedding_kernel(const int32_t* __restrict__ ids, const T* __restrict__ table, T* __restrict__ out,
+                                 int hidden) {
+    const uint4* src = reinterpret_cast<const uint4*>(table + (size_t)ids[blockIdx.x] * hidden);
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)blockIdx.x * hidden);
+    for (int i = threadIdx.x; i < hidden / 8; i += blockDim.x) dst[i] = src[i];
+}
+
+// greedy sampling: argmax over the vocabulary, lowest index wins ties (torch.argmax semantics used by
+// /root/reference/rtp_llm/models_py/bindings/core/CudaSampleOp.cc:330,453). One CTA per row.
+template <typename T>
+__global__ void argmax_kernel(const T* __restrict__ logits, int vocab, int32_t* __restrict__ out) {
+    __shared__ float s_v[32];
+    __shared__ int s_i[32];
+    const T* row = logits + (size_t)blockIdx.x * vocab;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < vocab; i += blockDim.x) {
+        const float v = to_f32<T>(row[i]);
+        if (v > bv || (v == bv && i < bi)) {
+            bv = v;
+            bi = i;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) {
+            bv = ov;
+            bi = oi;
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_v[threadIdx.x >> 5] = bv;
+        s_i[threadIdx.x >> 5] = bi;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        bv = threadIdx.x < (blockDim.x >> 5) ? s_v[threadIdx.x] : -INFINITY;
+        bi = threadIdx.x < (blockDim.x >> 5) ? s_i[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) {
+                bv = ov;
+                bi = oi;
+            }
+        }
+        if (threadIdx.x == 0) out[blockIdx.x] = bi;
+    }
+}
+// ---------------------------------------------------------------------------------------------- naive references
+// (GPU-side checkers for the parity tests; CUDA cores only, no tiling, obviously-correct indexing)
+template <typename T>
+__global__ void ref_paged_decode_attn_kernel(const T* __restrict__ q, T* __restrict__ out,
+                                             const T* __restrict__ kv_pool, const int32_t* __restrict__ page_list,
+                                             const int32_t* __restrict__ seq_lens, int Hq, int Hkv, int D, int M,
+                                             int tokens_per_block, float scale) {
+    // one warp per (b, h); online softmax in fp32; lanes split the head dim
+    const int b = blockIdx.x, h = blockIdx.y, lane = threadIdx.x;
+    const int kvh = h / (Hq / Hkv), len = seq_lens[b] + 1;
+    const size_t page_elems = (size_t)Hkv * tokens_per_block * D;
+    const int per = D / 32;  // <= 8
+    float qf[8], acc[8];
+    for (int j = 0; j < per; ++j) {
+        qf[j] = to_f32<T>(q[((size_t)b * Hq + h) * D + lane * per + j]);
+        acc[j] = 0.f;
+    }
+    float m = -INFINITY, l = 0.f;
+    for (int t = 0; t < len; ++t) {
+        const size_t in_page = ((size_t)kvh * tokens_per_block + t % tokens_per_block) * D;
+        const T* kr = kv_pool + (size_t)page_list[((size_t)b * 2 + 0) * M + t / tokens_per_block] * page_elems + in_page;
+        const T* vr = kv_pool + (size_t)page_list[((size_t)b * 2 + 1) * M + t / tokens_per_block] * page_elems + in_page;
+        float s = 0.f;
+        for (int j = 0; j < per; ++j) s += qf[j] * to_f32<T>(kr[lane * per + j]);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        s *= scale;
+        const float mn = fmaxf(m, s), a = expf(m - mn), pw = expf(s - mn);
+        l = l * a + pw;
+        for (int j = 0; j < per; ++j) acc[j] = acc[j] * a + pw * to_f32<T>(vr[lane * per + j]);
+        m = mn;
+    }
+    for (int j = 0; j < per; ++j) out[((size_t)b * Hq + h) * D + lane * per + j] = from_f32<T>(acc[j] / l);
+}
+
+// Y = X . W' from the UN-permuted reference tensors (fmt 0: W[K][N] T; 1: q int8 [K][N] + scale[N]; 2: q_packed [K][N/2]
+// + scales/zs [K/g][N]); one thread per output, fp32 accumulate, W' rounded to T exactly like the oracle.
+template <typename T>
+__global__ void ref_dequant_gemm_kernel(const T* __restrict__ x, int B, int K, int N, int fmt,
+                                        const void* __restrict__ w, const T* __restrict__ scales,
+                                        const T* __restrict__ zs, int group, const T* __restrict__ bias,
+                                        T* __restrict__ y) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (n >= N) return;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) {
+        float wv;
+        if (fmt == 0) {
+            wv = to_f32<T>(reinterpret_cast<const T*>(w)[(size_t)k * N + n]);
+        } else if (fmt == 1) {
+            wv = to_f32<T>(from_f32<T>((float)reinterpret_cast<const int8_t*>(w)[(size_t)k * N + n] * to_f32<T>(scales[n])));
+        } else {
+            const uint8_t byte = reinterpret_cast<const uint8_t*>(w)[(size_t)k * (N / 2) + n / 2];
+            int nib = (n & 1) ? (byte >> 4) : (byte & 0xF);
+            nib = (nib & 8) ? nib - 16 : nib;
+            wv = to_f32<T>(from_f32<T>(fmaf((float)nib, to_f32<T>(scales[(size_t)(k / group) * N + n]),
+                                           to_f32<T>(zs[(size_t)(k / group) * N + n]))));
+        }
+        acc = fmaf(to_f32<T>(x[(size_t)b * K + k]), wv, acc);
+    }
+    if (bias) acc += to_f32<T>(bias[n]);
+    y[(size_t)b * N + n] = from_f32<T>(acc);
+}
+
+}  // namespace b200

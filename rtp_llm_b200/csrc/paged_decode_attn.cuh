@@ -1,0 +1,327 @@
+// Paged GQA decode attention for sm_100a.
+//
+// Replaces (same math, same cache layout, same page-list format):
+//   runXqa                      /root/reference/rtp_llm/models_py/bindings/cuda/ops/CudaXqa.h:65-84 (+CudaXqa.cc:124-221)
+//   XQA sm_90a kernel           /root/reference/3rdparty/xqa/mha_sm90.cu (cannot run on B200)
+//   FlashInferTRTLLMDecodeOp    /root/reference/rtp_llm/models_py/modules/factory/attention/cuda_impl/trtllm_gen.py:503-546
+//
+// Work decomposition (B200-first, not a port of XQA's warpgroup pipeline):
+//   grid = (nsplit, B*Hkv); one CTA owns (sequence b, kv head, a contiguous run of 64-token tiles).
+//   Warp 4 lane 0 = TMA producer: reads the K/V page ids of each tile from the page list and issues 4-D tensor-map
+//   loads (128-byte swizzle, one box per page and per 64-channel half) into a 3-stage shared-memory ring.
+//   Warps 0-3 = consumers: each takes 16 of the tile's 64 tokens, S = Q.K^T and O += P.V on the legacy tensor path
+//   (ldmatrix + mma.sync m16n8k16; the whole GQA group is packed into the MMA M dimension so every K/V byte is read
+//   from HBM exactly once), online softmax with quad-level shuffles, private running (m, l, O) per warp, merged
+//   through shared memory at the end.  Sequence splits are merged by the last-arriving CTA (semaphore), XQA-style.
+//   The kernel is HBM-bound: per CTA 96 KB of K/V in flight, two CTAs per SM.
+#pragma once
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int kAttnTile = 64;          // tokens per pipeline stage
+constexpr int kAttnStages = 3;
+constexpr int kAttnD = 128;            // head dim
+constexpr int kAttnConsumerWarps = 4;
+constexpr int kAttnThreads = (kAttnConsumerWarps + 1) * 32;
+constexpr int kAttnStageBytes = 4 * kAttnTile * 128;  // K lo/hi + V lo/hi halves, 8 KB each = 32 KB
+constexpr int kAttnORowStride = 136;   // floats; +8 banks per row -> conflict-free float2 stores
+constexpr int kAttnSmemBytes = kAttnStages * kAttnStageBytes + 1024 /*align*/ + 256 /*barriers etc*/;
+
+struct AttnParams {
+    const void* q;            // [B][Hq][D]
+    void* out;                // [B][Hq*D]
+    const int32_t* page_list; // [B][1][2][M]
+    const int32_t* seq_lens;  // [B] tokens already cached (the new token sits at this index)
+    int B, Hq, Hkv, group, M;
+    int T, log2T;             // tokens per page
+    int box_h, boxes_per_tile;
+    int nsplit, tiles_per_split;
+    float scale_log2;         // q_scale * D^-1/2 * log2(e)
+    float* ws_o;              // [B*Hkv][nsplit][group][D]
+    float* ws_ml;             // [B*Hkv][nsplit][group][2]
+    int* sem;                 // [B*Hkv], zero on entry, zero on exit
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kAttnThreads, 2)
+paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the 128B-swizzled boxes
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kAttnStages * kAttnStageBytes);
+    uint64_t* empty_bar = full_bar + kAttnStages;
+    int* s_flag = reinterpret_cast<int*>(empty_bar + kAttnStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x, bh = blockIdx.y;
+    const int b = bh / p.Hkv, kvh = bh % p.Hkv;
+
+    const int len = p.seq_lens[b] + 1;
+    const int ntiles = (len + kAttnTile - 1) / kAttnTile;
+    const int t0 = split * p.tiles_per_split;
+    const int t1 = min(t0 + p.tiles_per_split, ntiles);
+    if (t0 >= t1) return;  // this split holds no tokens of this sequence (uniform for the CTA)
+    const int nact = (ntiles + p.tiles_per_split - 1) / p.tiles_per_split;  // CTAs that contribute to (b, kvh)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kAttnStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kAttnConsumerWarps);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == kAttnConsumerWarps) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            tma_prefetch_desc(&kv_map);
+            const int32_t* kpl = p.page_list + (size_t)(b * 2 + 0) * p.M;
+            const int32_t* vpl = p.page_list + (size_t)(b * 2 + 1) * p.M;
+            for (int i = t0; i < t1; ++i) {
+                const int it = i - t0, s = it % kAttnStages;
+                const uint32_t ph = (it / kAttnStages) & 1;
+                // page ids first (global loads overlap the wait below)
+                int kpage[4], vpage[4], inpage[4];
+                int nbox = 0;
+#pragma unroll
+                for (int bx = 0; bx < 4; ++bx) {
+                    const int tok = i * kAttnTile + bx * p.box_h;
+                    if (bx < p.boxes_per_tile && tok < len) {
+                        const int pidx = tok >> p.log2T;
+                        kpage[bx] = kpl[pidx];
+                        vpage[bx] = vpl[pidx];
+                        inpage[bx] = tok & (p.T - 1);
+                        nbox = bx + 1;
+                    }
+                }
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* stage = smem + s * kAttnStageBytes;
+                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(nbox * 4 * p.box_h * 128));
+#pragma unroll
+                for (int bx = 0; bx < 4; ++bx) {
+                    if (bx < nbox) {
+                        const int row_off = bx * p.box_h * 128;
+                        tma_load_4d(stage + 0 * 8192 + row_off, &kv_map, 0, inpage[bx], kvh, kpage[bx], &full_bar[s]);
+                        tma_load_4d(stage + 1 * 8192 + row_off, &kv_map, 64, inpage[bx], kvh, kpage[bx], &full_bar[s]);
+                        tma_load_4d(stage + 2 * 8192 + row_off, &kv_map, 0, inpage[bx], kvh, vpage[bx], &full_bar[s]);
+                        tma_load_4d(stage + 3 * 8192 + row_off, &kv_map, 64, inpage[bx], kvh, vpage[bx], &full_bar[s]);
+                    }
+                }
+            }
+        }
+        return;  // the producer warp takes no part in the merge (named barrier 1 counts 128 threads)
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    const int qrow = lane >> 2;          // fragment row (and row + 8)
+    const int qcol = (lane & 3) * 2;     // fragment column pair
+    // Q fragments for the whole head dim: 8 k-steps x 4 regs. Rows >= group are zero.
+    uint32_t qf[8][4];
+    {
+        const T* qbase = reinterpret_cast<const T*>(p.q) + ((size_t)b * p.Hq + (size_t)kvh * p.group) * kAttnD;
+        const bool v0 = qrow < p.group, v1 = (qrow + 8) < p.group;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const int c = kk * 16 + qcol;
+            qf[kk][0] = v0 ? *reinterpret_cast<const uint32_t*>(qbase + (size_t)qrow * kAttnD + c) : 0u;
+            qf[kk][1] = v1 ? *reinterpret_cast<const uint32_t*>(qbase + (size_t)(qrow + 8) * kAttnD + c) : 0u;
+            qf[kk][2] = v0 ? *reinterpret_cast<const uint32_t*>(qbase + (size_t)qrow * kAttnD + c + 8) : 0u;
+            qf[kk][3] = v1 ? *reinterpret_cast<const uint32_t*>(qbase + (size_t)(qrow + 8) * kAttnD + c + 8) : 0u;
+        }
+    }
+
+    float o[16][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY;  // running max (raw score units) for rows qrow / qrow+8
+    float l0 = 0.f, l1 = 0.f;              // per-thread partial row sums (quad-reduced at the end)
+    const float sl2 = p.scale_log2;
+
+    // ldmatrix lane geometry
+    const int mi = lane >> 3, mr = lane & 7;
+    const int k_tokrow = warp * 16 + (mi >> 1) * 8 + mr;  // K: matrices (tok0-7,c),(tok0-7,c+1),(tok8-15,c),(tok8-15,c+1)
+    const int k_chunk_add = mi & 1;
+    const int v_tokrow = warp * 16 + (mi & 1) * 8 + mr;   // V (trans): (tok0-7,c),(tok8-15,c),(tok0-7,c+1),(tok8-15,c+1)
+    const int v_chunk_add = mi >> 1;
+
+    for (int i = t0; i < t1; ++i) {
+        const int it = i - t0, s = it % kAttnStages;
+        const uint32_t ph = (it / kAttnStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        uint8_t* stage = smem + s * kAttnStageBytes;
+        const uint32_t k_base = smem_u32(stage), v_base = k_base + 2 * 8192;
+
+        const int tok0 = i * kAttnTile + warp * 16;
+        const int valid = len - tok0;  // tokens of this warp's slice that exist (may be <= 0)
+        if (valid < 16) {
+            // Rows past the end of the sequence hold stale / never-written bytes: P is 0 there but 0 * NaN = NaN,
+            // so the V rows are zeroed before use (K garbage is masked on the scores below).
+            const int first = valid < 0 ? 0 : valid;
+            for (int r = first; r < 16; ++r) {
+                uint8_t* row = stage + 2 * 8192 + (warp * 16 + r) * 128;
+                reinterpret_cast<uint32_t*>(row)[lane] = 0u;
+                reinterpret_cast<uint32_t*>(row + 8192)[lane] = 0u;
+            }
+            __syncwarp();
+        }
+
+        // ---- S = Q K^T for 16 heads x 16 tokens
+        float sc[2][4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const int half = kk >> 2, c = (kk & 3) * 2 + k_chunk_add;
+            uint32_t kb[4];
+            ldmatrix_x4(kb, k_base + half * 8192 + k_tokrow * 128 + ((c ^ (k_tokrow & 7)) << 4));
+            mma_m16n8k16<T>(sc[0], qf[kk], kb[0], kb[1]);
+            mma_m16n8k16<T>(sc[1], qf[kk], kb[2], kb[3]);
+        }
+
+        // ---- mask + online softmax (rows qrow and qrow+8)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const bool ok = (j * 8 + qcol + e) < valid;
+                sc[j][e] = ok ? sc[j][e] : -INFINITY;
+                sc[j][2 + e] = ok ? sc[j][2 + e] : -INFINITY;
+                mx0 = fmaxf(mx0, sc[j][e]);
+                mx1 = fmaxf(mx1, sc[j][2 + e]);
+            }
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        // a fully masked slice keeps m = -inf; use 0 as the subtrahend so exp2(-inf - 0) = 0 (no NaN)
+        const float ms0 = (mn0 == -INFINITY) ? 0.f : mn0 * sl2, ms1 = (mn1 == -INFINITY) ? 0.f : mn1 * sl2;
+        const float a0 = fast_exp2(m0 * sl2 - ms0), a1 = fast_exp2(m1 * sl2 - ms1);  // m = -inf -> 0
+        m0 = mn0;
+        m1 = mn1;
+        float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                sc[j][e] = fast_exp2(fmaf(sc[j][e], sl2, -ms0));
+                sc[j][2 + e] = fast_exp2(fmaf(sc[j][2 + e], sl2, -ms1));
+                ps0 += sc[j][e];
+                ps1 += sc[j][2 + e];
+            }
+        }
+        l0 = fmaf(l0, a0, ps0);
+        l1 = fmaf(l1, a1, ps1);
+        if (a0 != 1.f || a1 != 1.f) {
+#pragma unroll
+            for (int n = 0; n < 16; ++n) {
+                o[n][0] *= a0;
+                o[n][1] *= a0;
+                o[n][2] *= a1;
+                o[n][3] *= a1;
+            }
+        }
+        // P (rounded to the cache element type, 3rdparty/xqa/ref.py:80) as the A fragment of the second product
+        uint32_t pf[4];
+        pf[0] = pack2<T>(sc[0][0], sc[0][1]);
+        pf[1] = pack2<T>(sc[0][2], sc[0][3]);
+        pf[2] = pack2<T>(sc[1][0], sc[1][1]);
+        pf[3] = pack2<T>(sc[1][2], sc[1][3]);
+
+        // ---- O += P V
+#pragma unroll
+        for (int n2 = 0; n2 < 8; ++n2) {
+            const int half = n2 >> 2, c = (n2 & 3) * 2 + v_chunk_add;
+            uint32_t vb[4];
+            ldmatrix_x4_trans(vb, v_base + half * 8192 + v_tokrow * 128 + ((c ^ (v_tokrow & 7)) << 4));
+            mma_m16n8k16<T>(o[2 * n2], pf, vb[0], vb[1]);
+            mma_m16n8k16<T>(o[2 * n2 + 1], pf, vb[2], vb[3]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+
+    // quad-reduce the row sums
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+
+    // ---------------------------------------------------------------------- merge the 4 warps through smem
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done reading the K/V ring
+    float* o_s = reinterpret_cast<float*>(smem);                              // [4][16][kAttnORowStride]
+    float* m_s = o_s + kAttnConsumerWarps * 16 * kAttnORowStride;             // [4][16]
+    float* l_s = m_s + kAttnConsumerWarps * 16;                               // [4][16]
+    {
+        float* ow = o_s + (size_t)warp * 16 * kAttnORowStride;
+#pragma unroll
+        for (int n = 0; n < 16; ++n) {
+            *reinterpret_cast<float2*>(ow + qrow * kAttnORowStride + n * 8 + qcol) = make_float2(o[n][0], o[n][1]);
+            *reinterpret_cast<float2*>(ow + (qrow + 8) * kAttnORowStride + n * 8 + qcol) = make_float2(o[n][2], o[n][3]);
+        }
+        if ((lane & 3) == 0) {
+            m_s[warp * 16 + qrow] = m0;
+            m_s[warp * 16 + qrow + 8] = m1;
+            l_s[warp * 16 + qrow] = l0;
+            l_s[warp * 16 + qrow + 8] = l1;
+        }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+
+    const int d = threadIdx.x;  // 0..127: one output channel per thread
+    const size_t ws_base = ((size_t)bh * p.nsplit + split) * p.group;
+    T* outp = reinterpret_cast<T*>(p.out) + ((size_t)b * p.Hq + (size_t)kvh * p.group) * kAttnD;
+    for (int r = 0; r < p.group; ++r) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < kAttnConsumerWarps; ++w) m = fmaxf(m, m_s[w * 16 + r]);
+        float acc = 0.f, l = 0.f;
+#pragma unroll
+        for (int w = 0; w < kAttnConsumerWarps; ++w) {
+            const float f = fast_exp2((m_s[w * 16 + r] - m) * sl2);  // -inf -> 0 (m is finite: the CTA owns >= 1 token)
+            acc = fmaf(f, o_s[((size_t)w * 16 + r) * kAttnORowStride + d], acc);
+            l = fmaf(f, l_s[w * 16 + r], l);
+        }
+        if (nact == 1) {
+            outp[(size_t)r * kAttnD + d] = from_f32<T>(acc / l);
+        } else {
+            p.ws_o[(ws_base + r) * kAttnD + d] = acc;
+            if (d == 0) {
+                p.ws_ml[(ws_base + r) * 2 + 0] = m;
+                p.ws_ml[(ws_base + r) * 2 + 1] = l;
+            }
+        }
+    }
+    if (nact == 1) return;
+
+    // ---------------------------------------------------------------------- cross-CTA merge: last arriver reduces
+    __threadfence();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 0) {
+        const int prev = atomicAdd(&p.sem[bh], 1);
+        *s_flag = (prev == nact - 1);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (!*s_flag) return;
+    __threadfence();
+    for (int r = 0; r < p.group; ++r) {
+        float m = -INFINITY;
+        for (int sp = 0; sp < nact; ++sp)
+            m = fmaxf(m, __ldcg(&p.ws_ml[(((size_t)bh * p.nsplit + sp) * p.group + r) * 2 + 0]));
+        float acc = 0.f, l = 0.f;
+        for (int sp = 0; sp < nact; ++sp) {
+            const size_t row = ((size_t)bh * p.nsplit + sp) * p.group + r;
+            const float f = fast_exp2((__ldcg(&p.ws_ml[row * 2 + 0]) - m) * sl2);
+            acc = fmaf(f, __ldcg(&p.ws_o[row * kAttnD + d]), acc);
+            l = fmaf(f, __ldcg(&p.ws_ml[row * 2 + 1]), l);
+        }
+        outp[(size_t)r * kAttnD + d] = from_f32<T>(acc / l);
+    }
+    if (threadIdx.x == 0) p.sem[bh] = 0;  // self-reset for the next launch
+}
+
+}  // namespace b200

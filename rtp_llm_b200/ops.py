@@ -1,0 +1,224 @@
+"""Torch-tensor face of the C ABI. PyTorch is plumbing here (device memory + streams); all compute is in
+libb200_decode.so. Every function launches on the current CUDA stream and is CUDA-graph capturable."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import B200_FMT_F16, B200_FMT_INT4, B200_FMT_INT8, B200Error, check
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _is_bf16(t: torch.Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return 1
+    if t.dtype == torch.float16:
+        return 0
+    raise B200Error(f"unsupported activation dtype {t.dtype} (fp16 / bf16 only)")
+
+
+def _cuda_contig(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not (t.is_cuda and t.is_contiguous()):
+            raise B200Error("expected contiguous CUDA tensors")
+
+
+def device_check(device: int = 0) -> None:
+    check(_lib.load().b200_device_check(device), "b200_device_check")
+
+
+def launch_count() -> int:
+    return int(_lib.load().b200_launch_count())
+
+
+# ------------------------------------------------------------------------------------------------ indexing
+def convert_block_table(block_ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[B,M] int32 -> [B,1,2,M] int32 page list (XQAAttnOp::prepare, XQAAttnOp.cc:77-92)."""
+    _cuda_contig(block_ids, out)
+    B, M = block_ids.shape
+    if out is None:
+        out = torch.empty((B, 1, 2, M), dtype=torch.int32, device=block_ids.device)
+    check(_lib.load().b200_convert_block_table(_p(out), _p(block_ids), B, M, _stream()), "b200_convert_block_table")
+    return out
+
+
+def paged_attn_plan(sequence_lengths: torch.Tensor, block_ids: Optional[torch.Tensor], tokens_per_block: int,
+                    input_lengths: Optional[torch.Tensor] = None, prefix_lengths: Optional[torch.Tensor] = None):
+    ref = sequence_lengths if prefix_lengths is None else prefix_lengths
+    B = ref.shape[0]
+    dev = ref.device
+    M = block_ids.shape[1] if block_ids is not None else 0
+    ntok = B if prefix_lengths is None else int(input_lengths.sum().item())
+    last = torch.zeros(B, dtype=torch.int32, device=dev)
+    indptr = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+    indice = torch.zeros(max(B * M, 1), dtype=torch.int32, device=dev)
+    bidx = torch.zeros(max(ntok, 1), dtype=torch.int32, device=dev)
+    pos = torch.zeros(max(ntok, 1), dtype=torch.int32, device=dev)
+    check(_lib.load().b200_paged_attn_plan(_p(input_lengths), _p(sequence_lengths), _p(prefix_lengths), _p(block_ids), B,
+                                           M, tokens_per_block, _p(last), _p(indptr), _p(indice), _p(bidx), _p(pos),
+                                           _stream()), "b200_paged_attn_plan")
+    return dict(last_page_len=last, page_indptr=indptr, page_indice=indice, batch_indice=bidx[:ntok], positions=pos[:ntok])
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def attn_workspace(batch: int, head_num: int, kv_head_num: int, max_seq_len: int, device) -> torch.Tensor:
+    n = _lib.load().b200_paged_decode_attn_workspace_bytes(batch, head_num, kv_head_num, max_seq_len)
+    return torch.zeros(max(int(n), 256), dtype=torch.uint8, device=device)
+
+
+def paged_decode_attn(q: torch.Tensor, kv_cache_base: torch.Tensor, page_list: torch.Tensor,
+                      sequence_lengths: torch.Tensor, max_seq_len: int, workspace: torch.Tensor,
+                      out: Optional[torch.Tensor] = None, q_scale: float = 1.0) -> torch.Tensor:
+    """q [B,Hq,D] (or [B,Hq*D]); kv_cache_base [P,2,Hkv,T,D]; page_list [B,1,2,M]; sequence_lengths [B] int32 = tokens
+    already cached; max_seq_len = host bound on sequence_lengths+1. Returns [B, Hq*D]."""
+    _cuda_contig(q, kv_cache_base, page_list, workspace, out)
+    P, two, Hkv, T, D = kv_cache_base.shape
+    B = q.shape[0]
+    Hq = q.numel() // (B * D)
+    if out is None:
+        out = torch.empty((B, Hq * D), dtype=q.dtype, device=q.device)
+    check(_lib.load().b200_paged_decode_attn(_p(q), _is_bf16(q), _p(out), Hq, Hkv, D, B, page_list.shape[-1], max_seq_len,
+                                             T, _p(kv_cache_base), _p(page_list), _p(sequence_lengths), q_scale,
+                                             _p(workspace), workspace.numel(), _stream()), "b200_paged_decode_attn")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ weight-only GEMM
+class PackedWeight:
+    """A weight in the layout b200_wo_gemm consumes (+ what the epilogue needs)."""
+
+    def __init__(self, fmt: int, K: int, N: int, data: torch.Tensor, col_scale: Optional[torch.Tensor] = None):
+        self.fmt, self.K, self.N, self.data, self.col_scale = fmt, K, N, data, col_scale
+
+
+def pack_w4(q_packed: torch.Tensor, scales: torch.Tensor, zeros_x_scales: torch.Tensor, group: int = 128) -> PackedWeight:
+    """q_packed uint8/int8 [K,N/2], scales / zeros_x_scales [K/g,N] in the activation dtype (CUDA)."""
+    _cuda_contig(q_packed, scales, zeros_x_scales)
+    K, N = q_packed.shape[0], q_packed.shape[1] * 2
+    n = _lib.load().b200_wo_gemm_packed_bytes(B200_FMT_INT4, K, N)
+    if n == 0:
+        raise B200Error(f"pack_w4: unsupported shape K={K} N={N}")
+    blob = torch.empty(int(n), dtype=torch.uint8, device=q_packed.device)
+    check(_lib.load().b200_pack_w4(_p(q_packed), _p(scales), _p(zeros_x_scales), K, N, group, _p(blob), _stream()),
+          "b200_pack_w4")
+    return PackedWeight(B200_FMT_INT4, K, N, blob)
+
+
+def pack_w8(q: torch.Tensor, col_scale: torch.Tensor) -> PackedWeight:
+    _cuda_contig(q, col_scale)
+    K, N = q.shape
+    n = _lib.load().b200_wo_gemm_packed_bytes(B200_FMT_INT8, K, N)
+    if n == 0:
+        raise B200Error(f"pack_w8: unsupported shape K={K} N={N}")
+    blob = torch.empty(int(n), dtype=torch.uint8, device=q.device)
+    check(_lib.load().b200_pack_w8(_p(q), K, N, _p(blob), _stream()), "b200_pack_w8")
+    return PackedWeight(B200_FMT_INT8, K, N, blob, col_scale)
+
+
+def pack_f16(w_kn: torch.Tensor) -> PackedWeight:
+    """Reference stores W [K,N]; the kernel wants K contiguous -> one transpose at load time."""
+    K, N = w_kn.shape
+    return PackedWeight(B200_FMT_F16, K, N, w_kn.t().contiguous())
+
+
+def gemm_workspace(max_batch: int, shapes, device) -> torch.Tensor:
+    """One zero-filled scratch buffer big enough for every (K, N) in `shapes` (used serially on one stream)."""
+    n = max(int(_lib.load().b200_wo_gemm_workspace_bytes(max_batch, N, K)) for (K, N) in shapes)
+    return torch.zeros(max(n, 256), dtype=torch.uint8, device=device)
+
+
+def wo_gemm(x: torch.Tensor, w: PackedWeight, workspace: torch.Tensor, bias: Optional[torch.Tensor] = None,
+            out: Optional[torch.Tensor] = None, pdl: bool = False) -> torch.Tensor:
+    _cuda_contig(x, w.data, workspace, bias, out)
+    B, K = x.shape
+    if K != w.K:
+        raise B200Error(f"wo_gemm: x has K={K}, weight has K={w.K}")
+    if out is None:
+        out = torch.empty((B, w.N), dtype=x.dtype, device=x.device)
+    check(_lib.load().b200_wo_gemm(w.fmt, _is_bf16(x), _p(x), B, K, w.N, _p(w.data), _p(w.col_scale), _p(bias), _p(out),
+                                   _p(workspace), workspace.numel(), _lib.B200_GEMM_PDL if pdl else 0, _stream()),
+          "b200_wo_gemm")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ glue ops
+def add_rmsnorm(x, residual, gamma, eps, out=None):
+    _cuda_contig(x, residual, gamma, out)
+    rows, hidden = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.load().b200_add_rmsnorm(_p(x), _p(residual), _p(gamma), _p(out), _is_bf16(x), rows, hidden, eps, _stream()),
+          "b200_add_rmsnorm")
+    return out
+
+
+def silu_and_mul(gate_up, out=None):
+    _cuda_contig(gate_up, out)
+    rows, two_inter = gate_up.shape
+    if out is None:
+        out = torch.empty((rows, two_inter // 2), dtype=gate_up.dtype, device=gate_up.device)
+    check(_lib.load().b200_silu_and_mul(_p(gate_up), _p(out), _is_bf16(gate_up), rows, two_inter // 2, _stream()),
+          "b200_silu_and_mul")
+    return out
+
+
+def rope_append(qkv, kv_cache_base, page_list, sequence_lengths, head_num, rope_base, q_out=None):
+    _cuda_contig(qkv, kv_cache_base, page_list, sequence_lengths, q_out)
+    P, two, Hkv, T, D = kv_cache_base.shape
+    B = qkv.shape[0]
+    if q_out is None:
+        q_out = torch.empty((B, head_num * D), dtype=qkv.dtype, device=qkv.device)
+    check(_lib.load().b200_rope_append(_p(qkv), _p(q_out), _p(kv_cache_base), _p(page_list), _p(sequence_lengths),
+                                       _is_bf16(qkv), B, head_num, Hkv, D, page_list.shape[-1], T, rope_base, _stream()),
+          "b200_rope_append")
+    return q_out
+
+
+def embedding(ids, table, out=None):
+    _cuda_contig(ids, table, out)
+    rows, hidden = ids.shape[0], table.shape[1]
+    if out is None:
+        out = torch.empty((rows, hidden), dtype=table.dtype, device=table.device)
+    check(_lib.load().b200_embedding(_p(ids), _p(table), _p(out), _is_bf16(table), rows, hidden, _stream()), "b200_embedding")
+    return out
+
+
+def argmax(logits, out=None):
+    _cuda_contig(logits, out)
+    rows, vocab = logits.shape
+    dt = {torch.float16: 0, torch.bfloat16: 1, torch.float32: 2}[logits.dtype]
+    if out is None:
+        out = torch.empty(rows, dtype=torch.int32, device=logits.device)
+    check(_lib.load().b200_argmax(_p(logits), dt, rows, vocab, _p(out), _stream()), "b200_argmax")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ GPU-side checkers (tests only)
+def ref_paged_decode_attn(q, kv_cache_base, page_list, sequence_lengths, q_scale=1.0):
+    P, two, Hkv, T, D = kv_cache_base.shape
+    B = q.shape[0]
+    Hq = q.numel() // (B * D)
+    out = torch.empty((B, Hq * D), dtype=q.dtype, device=q.device)
+    check(_lib.load().b200_ref_paged_decode_attn(_p(q), _is_bf16(q), _p(out), Hq, Hkv, D, B, page_list.shape[-1], T,
+                                                 _p(kv_cache_base), _p(page_list), _p(sequence_lengths), q_scale,
+                                                 _stream()), "b200_ref_paged_decode_attn")
+    return out
+
+
+def ref_dequant_gemm(x, fmt, w, scales=None, zeros_x_scales=None, group=128, bias=None):
+    """fmt F16: w [K,N]; INT8: w int8 [K,N] + scales [N]; INT4: w uint8 [K,N/2] + scales/zeros [K/g,N]."""
+    B, K = x.shape
+    N = w.shape[1] * (2 if fmt == B200_FMT_INT4 else 1)
+    out = torch.empty((B, N), dtype=x.dtype, device=x.device)
+    check(_lib.load().b200_ref_dequant_gemm(fmt, _is_bf16(x), _p(x), B, K, N, _p(w), _p(scales), _p(zeros_x_scales), group,
+                                            _p(bias), _p(out), _stream()), "b200_ref_dequant_gemm")
+    return out
