@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- decode tokens/s of the B200 hot path (BASELINE.json metric) + roofline + CPU baseline.
+
+  python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" = one full decode step (all layers: 4 GEMMs + rope/append + paged attention + norms, lm_head, greedy argmax)
+for a batch of synthetic sequences under ONE CUDA graph.  Default workload = the configuration BASELINE.json's metric is
+quoted on: Llama-3-8B INT4-AWQ(g128), batch 32, context 2048, one B200.  N > 1 = the reference's tensor-parallel split
+(strong scaling: the same batch, weights/heads sharded, NCCL all-reduce after the row-parallel GEMMs).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "decode tokens/sec Llama-3-8B INT4-AWQ b32 ctx2048"
+UNIT = "tokens/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "qwen2-72b", "tiny"])
+    ap.add_argument("--quant", default="int4", choices=["int4", "int8", "f16"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--ctx", type=int, default=2048)
+    ap.add_argument("--pdl", type=int, default=int(os.environ.get("B200_PDL", "0")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def model_cfg(args):
+    import dataclasses
+    from rtp_llm_b200.decode_step import LLAMA3_8B, QWEN2_72B, TINY
+    base = {"llama3-8b": LLAMA3_8B, "qwen2-72b": QWEN2_72B, "tiny": TINY}[args.model]
+    return dataclasses.replace(base, quant=args.quant)
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_arm(args, cfg, budget_s=25.0):
+    """Times the CPU restatement (oracle/decode_oracle.c, OpenMP, all host threads) on a bounded sample of the SAME
+    workload: one decoder layer (attention over the full batch/context + its 4 GEMMs) and a slice of lm_head, then
+    extrapolates to the full step.  kind = "port": the reference snapshot has no CPU backend to compile."""
+    import numpy as np
+    from oracle import oracle as orc
+    orc.build()
+    cores = orc.num_threads()
+    rng = np.random.default_rng(0)
+    B, S, T = args.batch, args.ctx, cfg.tokens_per_block
+    Hq, Hkv, D, H, I = cfg.head_num, cfg.kv_head_num, cfg.head_dim, cfg.hidden, cfg.inter
+    M = (S + T - 1) // T
+    # attention, one layer
+    pool = (rng.standard_normal((B * M + 1, 2, Hkv, T, D), dtype=np.float32)).astype(np.float16).view(np.uint16)
+    q = rng.standard_normal((B, Hq, D), dtype=np.float32).astype(np.float16).view(np.uint16)
+    block_ids = (rng.permutation(B * M).astype(np.int32) + 1).reshape(B, M)
+    pl = orc.convert_block_table(block_ids)
+    seq = np.full(B, S - 1, np.int32)
+    t0 = time.perf_counter()
+    orc.paged_decode_attn(q, pool, pl, seq, Hq, Hkv, D, T)
+    t_attn = time.perf_counter() - t0
+    # GEMMs, one layer (column slices bound the sample; time scales linearly in N)
+    fmt = cfg.quant
+    t_gemm = 0.0
+    sample_desc = []
+    for (K, N) in ((H, (Hq + 2 * Hkv) * D), (Hq * D, H), (H, 2 * I), (I, H)):
+        Ns = min(N, 2048)
+        x = rng.standard_normal((B, K), dtype=np.float32).astype(np.float16).view(np.uint16)
+        if fmt == "int4":
+            w = rng.integers(0, 256, (K, Ns // 2), dtype=np.uint8)
+            s = (np.abs(rng.standard_normal((K // 128, Ns), dtype=np.float32)) * 0.01 + 1e-3).astype(np.float16)
+            kw = dict(scales=s, zeros_x_scales=s, group=128)
+        elif fmt == "int8":
+            w = rng.integers(-128, 128, (K, Ns), dtype=np.int8)
+            kw = dict(scales=np.full(Ns, 1e-3, np.float16))
+        else:
+            w = (rng.standard_normal((K, Ns), dtype=np.float32) * 0.02).astype(np.float16).view(np.uint16)
+            kw = {}
+        t0 = time.perf_counter()
+        orc.dequant_gemm(x, fmt, w, fast=True, **kw)
+        dt = time.perf_counter() - t0
+        t_gemm += dt * (N / Ns)
+        sample_desc.append(f"{K}x{Ns}/{N}")
+    # lm_head slice (fp16 weights)
+    Ns = 4096
+    x = rng.standard_normal((B, H), dtype=np.float32).astype(np.float16).view(np.uint16)
+    w = (rng.standard_normal((H, Ns), dtype=np.float32) * 0.02).astype(np.float16).view(np.uint16)
+    t0 = time.perf_counter()
+    orc.dequant_gemm(x, "f16", w, fast=True)
+    t_lm = (time.perf_counter() - t0) * (cfg.vocab / Ns)
+    t_step = cfg.layers * (t_attn + t_gemm) + t_lm
+    return dict(value=B / t_step, unit=UNIT, cores=cores, kind="port",
+                sample=(f"1 of {cfg.layers} layers timed (paged attention B{B} ctx{S} + 4 {fmt} GEMMs on column slices "
+                        f"{','.join(sample_desc)}) + lm_head slice {Ns}/{cfg.vocab}, extrapolated; "
+                        f"layer={1e3 * (t_attn + t_gemm):.0f} ms (attn {1e3 * t_attn:.0f} ms) lm_head={1e3 * t_lm:.0f} ms"),
+                ms_per_step=1e3 * t_step)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = model_cfg(args)
+    workload = f"{cfg.name} {cfg.quant}{'-AWQ g128' if cfg.quant == 'int4' else ''} decode, batch {args.batch}, ctx {args.ctx}"
+
+    if args.impl == "reference":
+        # the reference's CPU arm: rank 0 alone runs it, the other ranks exit 0 without work
+        if rank != 0:
+            return 0
+        cb = cpu_arm(args, cfg)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f16 activations, fp32 accumulate", "data": "synthetic",
+                "config": {"workload": workload, "parallelism": "cpu"},
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from rtp_llm_b200 import ops
+    from rtp_llm_b200.decode_step import DecodeStep
+    from rtp_llm_b200.tp import make_comm
+
+    assert world == args.gpus or world == 1, f"launched with WORLD_SIZE={world} but --gpus {args.gpus}"
+    tp = world
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ops.device_check(local_rank)
+    comm = None
+    if tp > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        comm = make_comm(dev)
+
+    model = DecodeStep(cfg, args.batch, args.ctx, dev, tp_rank=rank, tp_size=tp, comm=comm, pdl=bool(args.pdl))
+    launches_per_step = model.launches_per_step()
+    model.capture()
+
+    def barrier():
+        if tp > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput ("value"): graph replays only
+    for _ in range(max(args.warmup, 3)):
+        model.replay()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st.record()
+    for _ in range(args.steps):
+        model.replay()
+    en.record()
+    barrier()
+    ms = st.elapsed_time(en) / args.steps
+
+    # ---- end to end ("e2e"): host buffers -> H2D -> step -> D2H, every step, through the public call
+    for _ in range(3):
+        model.upload_inputs(); model.replay(); model.download_outputs()
+    barrier()
+    st.record()
+    for _ in range(args.steps):
+        model.upload_inputs()
+        model.replay()
+        model.download_outputs()
+        torch.cuda.current_stream(dev).synchronize()   # the caller needs the sampled tokens before the next step
+    en.record()
+    barrier()
+    ms_e2e = st.elapsed_time(en) / args.steps
+
+    # ---- dominant kernel (paged decode attention): average launch duration, CUDA events on the launching stream,
+    #      each launch reads a different layer's 268 MB of K/V (> L2), same inputs as inside the step
+    n_attn = 0
+    for _ in range(3):
+        ops.paged_decode_attn(model.q, model.layers[0]["kv"], model.page_list, model.seq_lens, model.ctx, model.attn_ws,
+                              out=model.attn)
+    torch.cuda.synchronize(dev)
+    st.record()
+    for _ in range(max(1, args.steps // 5)):
+        for L in model.layers:
+            ops.paged_decode_attn(model.q, L["kv"], model.page_list, model.seq_lens, model.ctx, model.attn_ws, out=model.attn)
+            n_attn += 1
+    en.record()
+    barrier()
+    attn_ms = st.elapsed_time(en) / n_attn
+    clocks = sampler.stop() if sampler else None
+
+    if tp > 1:
+        t = torch.tensor([ms, ms_e2e, attn_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e, attn_ms = t.tolist()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        ab = model.algorithmic_bytes()          # per GPU
+        attn_bytes = ab["kv"] / cfg.layers
+        achieved = attn_bytes / (attn_ms * 1e-3) / 1e9
+        step_gbs = ab["total"] / (ms * 1e-3) / 1e9
+        traffic = None
+        tfile = os.path.join(ROOT, "profiles", "attn_traffic_bytes.json")
+        if os.path.exists(tfile):
+            try:
+                traffic = json.load(open(tfile)).get(f"b{args.batch}_ctx{args.ctx}_tp{tp}")
+            except Exception:  # noqa: BLE001
+                traffic = None
+        line = {
+            "metric": METRIC, "value": args.batch / (ms * 1e-3), "unit": UNIT, "n_gpus": tp, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f16 activations x int4 weights, fp32 accumulate" if cfg.quant == "int4"
+            else f"f16 activations x {cfg.quant} weights, fp32 accumulate",
+            "data": "synthetic (random-init weights of the named architecture, random page tables)",
+            "config": {"workload": workload, "global_batch": args.batch, "seq_len": args.ctx,
+                       "parallelism": f"tp{tp}", "page_size": cfg.tokens_per_block, "cuda_graph": True,
+                       "l2": "inputs larger than L2 (each step streams %.2f GB of weights + KV per GPU)" % (ab["total"] / 1e9),
+                       "pdl": bool(args.pdl)},
+            "e2e": {"value": args.batch / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": model.h2d_bytes(),
+                    "d2h_bytes_per_step": model.d2h_bytes(), "ms_per_step": ms_e2e},
+            "gpu_launches": launches_per_step * args.steps,
+            "launches_per_step": launches_per_step,
+            "clocks": clocks,
+            "roofline": {"kernel": "paged_decode_attn_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "bytes_per_launch": attn_bytes, "us_per_launch": attn_ms * 1e3},
+            "step_roofline": {"algorithmic_bytes_per_gpu": ab["total"], "achieved_gbs": step_gbs, "frac": step_gbs / peak,
+                              "roofline_tokens_per_s": args.batch / (ab["total"] / (peak * 1e9)), "split": ab},
+        }
+        if not args.no_cpu_baseline and tp == 1:
+            cb = cpu_arm(args, cfg)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if tp > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,245 @@
+"""One decode step of a dense Llama/Qwen-style stack on the B200 hot path (synthetic weights, synthetic page tables).
+
+This is the measurement harness of SURVEY.md section 8(d): per layer
+    add_rmsnorm -> qkv GEMM -> rope + KV append -> paged decode attention -> o GEMM -> [TP all-reduce]
+    -> add_rmsnorm -> w13 GEMM -> SiLU*mul -> w2 GEMM -> [TP all-reduce]
+then final norm -> lm_head (fp16 weights) -> greedy argmax, all on one stream under one CUDA graph.
+It mirrors the call order of the reference's Python model graph (model_desc/qwen3.py:57-138,
+modules/hybrid/causal_attention.py:75-93, modules/hybrid/dense_mlp.py:95-106, PyWrappedModel.cc:938-1060) but owns none
+of its engine: scheduler, cache manager and sampler policy stay the reference's.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from ._lib import B200_FMT_F16, B200_FMT_INT4, B200_FMT_INT8
+
+
+@dataclasses.dataclass
+class ModelConfig:
+    name: str
+    hidden: int
+    layers: int
+    head_num: int
+    kv_head_num: int
+    head_dim: int
+    inter: int
+    vocab: int
+    rope_base: float = 500000.0
+    eps: float = 1e-5
+    quant: str = "int4"          # "f16" | "int8" | "int4"
+    tokens_per_block: int = 64   # KVCacheConfig.seq_size_per_block default (ConfigModules.h:174)
+
+
+LLAMA3_8B = ModelConfig("Llama-3-8B", 4096, 32, 32, 8, 128, 14336, 128256)
+QWEN2_72B = ModelConfig("Qwen2-72B", 8192, 80, 64, 8, 128, 29696, 152064, rope_base=1000000.0, eps=1e-6)  # GPTQ-padded inter
+TINY = ModelConfig("tiny", 512, 2, 4, 2, 128, 512, 1024, tokens_per_block=16)
+
+
+def _fmt(q: str) -> int:
+    return {"f16": B200_FMT_F16, "int8": B200_FMT_INT8, "int4": B200_FMT_INT4}[q]
+
+
+def weight_bytes(cfg: ModelConfig, K: int, N: int) -> float:
+    """Algorithmic HBM bytes of one weight (int4 = E/2 + (E/128)*4, int8 = E + 2N, f16 = 2E)."""
+    E = K * N
+    if cfg.quant == "int4":
+        return E / 2 + E / 128 * 4
+    if cfg.quant == "int8":
+        return E + 2 * N
+    return 2 * E
+
+
+class DecodeStep:
+    """Synthetic decode step. tp_size > 1 shards exactly as the reference's TP split (utils/model_weight.py:1489-1580):
+    qkv / w13 column-parallel, o / w2 row-parallel + all-reduce, lm_head vocab-parallel + all-gather."""
+
+    def __init__(self, cfg: ModelConfig, batch: int, ctx: int, device: torch.device, tp_rank: int = 0, tp_size: int = 1,
+                 dtype=torch.float16, seed: int = 0, keep_reference: bool = False, ragged: bool = False,
+                 pdl: bool = False, comm=None):
+        assert cfg.head_num % tp_size == 0 and cfg.inter % tp_size == 0
+        self.cfg, self.B, self.ctx, self.dev, self.dtype = cfg, batch, ctx, device, dtype
+        self.tp_rank, self.tp_size, self.comm, self.pdl = tp_rank, tp_size, comm, pdl
+        self.Hq = cfg.head_num // tp_size
+        self.Hkv = max(cfg.kv_head_num // tp_size, 1)   # kv heads replicated when Hkv < tp (MHAKVCacheSpec.h:46-51)
+        self.D = cfg.head_dim
+        self.inter = cfg.inter // tp_size
+        assert (self.inter % 128 == 0) and (self.Hq * self.D) % 128 == 0, "row-parallel K must be a multiple of 128"
+        self.vocab = (cfg.vocab + tp_size - 1) // tp_size
+        self.vocab = (self.vocab + 7) // 8 * 8          # sp_0_pad8
+        T = cfg.tokens_per_block
+        self.M = (ctx + T - 1) // T
+        self.ref: Dict[str, list] = {} if keep_reference else None
+        g = torch.Generator(device="cpu").manual_seed(seed * 1000 + 17)
+        H = cfg.hidden
+
+        def make_weight(K: int, N: int, gen_seed: int, quant: Optional[str] = None):
+            quant = quant or cfg.quant
+            gg = torch.Generator(device=device).manual_seed(gen_seed)
+            if quant == "int4":
+                qp = torch.randint(0, 256, (K, N // 2), generator=gg, device=device, dtype=torch.uint8)
+                s = (torch.randn(K // 128, N, generator=gg, device=device).abs() * 0.01 + 1e-3).to(dtype)
+                z = torch.randint(0, 16, (K // 128, N), generator=gg, device=device)
+                zs = ((8 - z).to(dtype) * s).to(dtype)
+                w = ops.pack_w4(qp, s, zs)
+                refw = ("int4", qp, s, zs)
+            elif quant == "int8":
+                q8 = torch.randint(-128, 128, (K, N), generator=gg, device=device, dtype=torch.int8)
+                s = (torch.randn(N, generator=gg, device=device).abs() * 2e-4 + 1e-5).to(dtype)
+                w = ops.pack_w8(q8, s)
+                refw = ("int8", q8, s, None)
+            else:
+                wkn = (torch.randn(K, N, generator=gg, device=device) * 0.02).to(dtype)
+                w = ops.pack_f16(wkn)
+                refw = ("f16", wkn, None, None)
+            return w, (tuple(t.cpu() if torch.is_tensor(t) else t for t in refw) if keep_reference else None)
+
+        self.layers: List[dict] = []
+        qkv_n = (self.Hq + 2 * self.Hkv) * self.D
+        for l in range(cfg.layers):
+            base = (seed * 100003 + l) * 16 + tp_rank * 7919
+            L = {}
+            L["qkv"], r0 = make_weight(H, qkv_n, base + 1)
+            L["o"], r1 = make_weight(self.Hq * self.D, H, base + 2)
+            L["w13"], r2 = make_weight(H, 2 * self.inter, base + 3)
+            L["w2"], r3 = make_weight(self.inter, H, base + 4)
+            L["ln1"] = (1.0 + 0.1 * torch.randn(H, generator=g)).to(dtype).to(device)
+            L["ln2"] = (1.0 + 0.1 * torch.randn(H, generator=g)).to(dtype).to(device)
+            L["kv"] = None
+            if keep_reference:
+                L["ref"] = dict(qkv=r0, o=r1, w13=r2, w2=r3)
+            self.layers.append(L)
+        self.final_ln = (1.0 + 0.1 * torch.randn(H, generator=g)).to(dtype).to(device)
+        self.lm_head, self.lm_head_ref = make_weight(H, self.vocab, seed * 100003 + 999983 + tp_rank, quant="f16")
+        gg = torch.Generator(device=device).manual_seed(seed + 5)
+        self.embed = (torch.randn(cfg.vocab, H, generator=gg, device=device) * 0.5).to(dtype)
+
+        # ---- paged KV cache: P = B*M + 1 pages per layer, block 0 reserved, random permutation of the rest
+        P = batch * self.M + 1
+        gk = torch.Generator(device=device).manual_seed(42)
+        for L in self.layers:
+            L["kv"] = torch.randn(P, 2, self.Hkv, T, self.D, generator=gk, device=device).to(dtype)
+        gp = torch.Generator().manual_seed(3)
+        perm = torch.randperm(P - 1, generator=gp).to(torch.int32) + 1
+        self.block_ids_h = perm.reshape(batch, self.M).contiguous().pin_memory()
+        if ragged:
+            gl = torch.Generator().manual_seed(4)
+            lens = torch.randint(ctx // 2, ctx + 1, (batch,), generator=gl)
+        else:
+            lens = torch.full((batch,), ctx)
+        self.seq_lens_h = (lens - 1).to(torch.int32).pin_memory()       # tokens already cached
+        self.ids_h = torch.randint(0, cfg.vocab, (batch,), generator=gp).to(torch.int32).pin_memory()
+        self.next_h = torch.zeros(batch, dtype=torch.int32).pin_memory()
+
+        # ---- static device buffers (graph-capturable: nothing is allocated inside step())
+        def buf(*shape, dt=dtype):
+            return torch.empty(*shape, dtype=dt, device=device)
+        self.ids = buf(batch, dt=torch.int32)
+        self.seq_lens = buf(batch, dt=torch.int32)
+        self.block_ids = buf(batch, self.M, dt=torch.int32)
+        self.page_list = buf(batch, 1, 2, self.M, dt=torch.int32)
+        self.resid = buf(batch, H)
+        self.x = buf(batch, H)
+        self.qkv = buf(batch, qkv_n)
+        self.q = buf(batch, self.Hq * self.D)
+        self.attn = buf(batch, self.Hq * self.D)
+        self.proj = buf(batch, H)
+        self.gu = buf(batch, 2 * self.inter)
+        self.act = buf(batch, self.inter)
+        self.logits = buf(batch, self.vocab)
+        self.logits_all = buf(tp_size, batch, self.vocab) if tp_size > 1 else None
+        self.next_ids = buf(batch, dt=torch.int32)
+        shapes = [(H, qkv_n), (self.Hq * self.D, H), (H, 2 * self.inter), (self.inter, H), (H, self.vocab)]
+        self.gemm_ws = ops.gemm_workspace(batch, shapes, device)
+        self.attn_ws = ops.attn_workspace(batch, self.Hq, self.Hkv, ctx, device)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.upload_inputs()
+        torch.cuda.synchronize(device)
+
+    # ------------------------------------------------------------------ host <-> device
+    def upload_inputs(self):
+        """H2D of one step's inputs from pinned host memory (token ids, lengths, block table)."""
+        self.ids.copy_(self.ids_h, non_blocking=True)
+        self.seq_lens.copy_(self.seq_lens_h, non_blocking=True)
+        self.block_ids.copy_(self.block_ids_h, non_blocking=True)
+
+    def download_outputs(self):
+        self.next_h.copy_(self.next_ids, non_blocking=True)
+
+    def h2d_bytes(self) -> int:
+        return self.ids_h.numel() * 4 + self.seq_lens_h.numel() * 4 + self.block_ids_h.numel() * 4
+
+    def d2h_bytes(self) -> int:
+        return self.next_h.numel() * 4
+
+    # ------------------------------------------------------------------ the step
+    def _all_reduce(self, t: torch.Tensor):
+        if self.tp_size > 1:
+            self.comm.all_reduce(t)
+
+    def step(self):
+        cfg = self.cfg
+        ops.convert_block_table(self.block_ids, out=self.page_list)
+        ops.embedding(self.ids, self.embed, out=self.resid)
+        first = True
+        for L in self.layers:
+            if first:
+                ops.add_rmsnorm(self.resid, None, L["ln1"], cfg.eps, out=self.x)
+                first = False
+            else:
+                ops.add_rmsnorm(self.proj, self.resid, L["ln1"], cfg.eps, out=self.x)
+            ops.wo_gemm(self.x, L["qkv"], self.gemm_ws, out=self.qkv, pdl=self.pdl)
+            ops.rope_append(self.qkv, L["kv"], self.page_list, self.seq_lens, self.Hq, cfg.rope_base, q_out=self.q)
+            ops.paged_decode_attn(self.q, L["kv"], self.page_list, self.seq_lens, self.ctx, self.attn_ws, out=self.attn)
+            ops.wo_gemm(self.attn, L["o"], self.gemm_ws, out=self.proj, pdl=self.pdl)
+            self._all_reduce(self.proj)
+            ops.add_rmsnorm(self.proj, self.resid, L["ln2"], cfg.eps, out=self.x)
+            ops.wo_gemm(self.x, L["w13"], self.gemm_ws, out=self.gu, pdl=self.pdl)
+            ops.silu_and_mul(self.gu, out=self.act)
+            ops.wo_gemm(self.act, L["w2"], self.gemm_ws, out=self.proj, pdl=self.pdl)
+            self._all_reduce(self.proj)
+        ops.add_rmsnorm(self.proj, self.resid, self.final_ln, cfg.eps, out=self.x)
+        ops.wo_gemm(self.x, self.lm_head, self.gemm_ws, out=self.logits, pdl=self.pdl)
+        if self.tp_size > 1:
+            self.comm.all_gather(self.logits_all, self.logits)
+            full = self.logits_all.permute(1, 0, 2).reshape(self.B, -1)
+            self.next_ids.copy_(torch.argmax(full.float(), dim=-1).to(torch.int32))  # next: own kernel over the gathered view
+        else:
+            ops.argmax(self.logits, out=self.next_ids)
+
+    def launches_per_step(self) -> int:
+        n0 = ops.launch_count()
+        self.step()
+        return ops.launch_count() - n0
+
+    def capture(self):
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self.step()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.step()
+        torch.cuda.synchronize(self.dev)
+
+    def replay(self):
+        self.graph.replay()
+
+    # ------------------------------------------------------------------ accounting
+    def algorithmic_bytes(self) -> Dict[str, float]:
+        cfg, H = self.cfg, self.cfg.hidden
+        qkv_n = (self.Hq + 2 * self.Hkv) * self.D
+        w = (weight_bytes(cfg, H, qkv_n) + weight_bytes(cfg, self.Hq * self.D, H) + weight_bytes(cfg, H, 2 * self.inter)
+             + weight_bytes(cfg, self.inter, H)) * cfg.layers
+        lens = (self.seq_lens_h.to(torch.int64) + 1).sum().item()
+        kv = 2.0 * lens * self.Hkv * self.D * 2 * cfg.layers
+        lm = 2.0 * H * self.vocab
+        return dict(weights=w, kv=kv, lm_head=lm, total=w + kv + lm)

@@ -1,0 +1,50 @@
+"""CPU test: libb200_decode.so loads and exports every symbol include/b200_decode_ops.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+from rtp_llm_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "b200_decode_ops.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    names = _declared()
+    assert len(names) >= 19
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    # and the ctypes signature table covers exactly the header
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_argument_errors_are_reported_not_crashed():
+    lib = _lib.load()
+    # null pointers / bad shapes are rejected on the host before any CUDA call
+    assert lib.b200_convert_block_table(None, None, 4, 8, None) == -1
+    assert b"null" in lib.b200_last_error()
+    assert lib.b200_wo_gemm_packed_bytes(_lib.B200_FMT_INT4, 100, 64) == 0          # K not a multiple of 128
+    assert lib.b200_wo_gemm_packed_bytes(_lib.B200_FMT_INT4, 256, 256) == 2 * 2 * 8704
+    assert lib.b200_wo_gemm_packed_bytes(_lib.B200_FMT_INT8, 256, 200) == 2 * 2 * 16384   # N padded to 128-feature tiles
+    assert lib.b200_paged_decode_attn_workspace_bytes(32, 32, 8, 2048) > 0
+    assert lib.b200_wo_gemm_workspace_bytes(32, 4096, 4096) >= 16384
+
+
+def test_sass_uses_the_blackwell_paths():
+    """The built library must contain tcgen05 MMA, TMEM ld/st and TMA instructions (SASS mnemonics of B200_PROFILING.md)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        import pytest
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", build.build()], capture_output=True, text=True).stdout
+    for mnem in ("UTCHMMA", "STTM", "LDTM", "UTMALDG", "UBLKCP"):
+        assert mnem in sass, mnem

@@ -1,0 +1,125 @@
+"""GPU parity tests (run by the driver with -m gpu on a B200). Everything goes through the C ABI
+(rtp_llm_b200.ops -> libb200_decode.so) and is compared with the CPU oracle on the same seeded inputs, with the golden
+fixtures the reference's code produced, and -- at BASELINE.json's full sizes -- with a deliberately naive GPU kernel."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as orc  # noqa: E402
+from rtp_llm_b200 import ops  # noqa: E402
+from rtp_llm_b200._lib import B200_FMT_F16, B200_FMT_INT4, B200_FMT_INT8  # noqa: E402
+from tools import gpu_probe as probe  # noqa: E402
+
+
+def _run(fn, *a, **k):
+    probe.RESULTS.clear()
+    fn(*a, **k)
+    bad = [n for n, ok in probe.RESULTS if not ok]
+    assert probe.RESULTS and not bad, bad
+
+
+def test_native_library_is_the_path_that_runs():
+    ops.device_check(0)
+    n0 = ops.launch_count()
+    ops.convert_block_table(torch.zeros(2, 4, dtype=torch.int32, device="cuda"))
+    assert ops.launch_count() == n0 + 1
+
+
+@pytest.mark.parametrize("name", ["attn_p16_gqa4", "attn_p64_gqa8", "attn_p32_mha"])
+def test_attention_matches_reference_golden(golden_dir, name):
+    """Fixtures produced by the reference's own torch oracle (oracle/make_golden.py); tolerance = the reference's
+    rtol = atol = 1e-2 (base_attention_test.py:147-148)."""
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    dev = torch.device("cuda")
+    q = torch.from_numpy(g["q"]).to(dev)
+    pool = torch.from_numpy(g["kv_pool"]).to(dev)
+    bid = torch.from_numpy(g["block_ids"]).to(dev)
+    seq = torch.from_numpy(g["sequence_lengths"]).to(dev)
+    pl = ops.convert_block_table(bid)
+    max_len = int(g["sequence_lengths"].max()) + 1
+    ws = ops.attn_workspace(q.shape[0], int(g["head_num"]), int(g["kv_head_num"]), max_len, dev)
+    out = ops.paged_decode_attn(q, pool, pl, seq, max_len, ws)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.float().cpu().numpy(), g["expect"], rtol=1e-2, atol=1e-2)
+
+
+ATTN_CASES = [
+    ("B1 len1", 1, 4, 1, 64, [1], torch.float16, None),
+    ("len 10/64", 2, 8, 2, 64, [10, 64], torch.float16, None),                     # test_xqa.py:368-449 shapes
+    ("len 65..513", 4, 8, 2, 64, [65, 128, 200, 513], torch.float16, None),
+    ("page16", 4, 8, 2, 16, [10, 20, 65, 130], torch.float16, None),
+    ("page32 mha", 3, 4, 4, 32, [64, 65, 1], torch.float16, None),
+    ("page128 g8", 3, 16, 2, 128, [127, 129, 300], torch.float16, None),
+    ("g16", 2, 16, 1, 64, [100, 257], torch.float16, None),
+    ("bf16", 3, 8, 2, 64, [63, 64, 300], torch.bfloat16, None),
+    ("split every tile", 3, 8, 2, 64, [63, 64, 700], torch.float16, {"B200_ATTN_TILES_PER_SPLIT": 1}),
+    ("no split", 3, 8, 2, 64, [63, 64, 700], torch.float16, {"B200_ATTN_TILES_PER_SPLIT": 1000}),
+]
+
+
+@pytest.mark.parametrize("case", ATTN_CASES, ids=[c[0] for c in ATTN_CASES])
+def test_attention_vs_oracle(case):
+    name, B, Hq, Hkv, T, lens, dtype, env = case
+    _run(probe.attn_vs_oracle, name, B, Hq, Hkv, T, lens, dtype, env)
+
+
+@pytest.mark.parametrize("cfg", [("Llama-3-8B B32 S2048", 32, 32, 8, 64, 2048, False),
+                                 ("Llama-3-8B B32 S2048 ragged", 32, 32, 8, 64, 2048, True),
+                                 ("Qwen2-72B TP8 B16 S8192", 16, 8, 1, 64, 8192, False)], ids=lambda c: c[0])
+def test_attention_full_size_vs_naive_gpu_kernel(cfg):
+    name, B, Hq, Hkv, T, S, ragged = cfg
+    _run(probe.attn_vs_ref_big, name, B, Hq, Hkv, T, S, torch.float16, ragged)
+
+
+GEMM_SMALL = [
+    ("onehot", 16, 128, 128, dict(simple=True, onehot=True)),
+    ("B16 K256 N256", 16, 256, 256, {}),
+    ("B5 K512 N384 bias", 5, 512, 384, dict(bias=True)),
+    ("splitk4", 32, 1024, 256, dict(env={"B200_GEMM_SPLITK": 4})),
+    ("ragged N bpad64", 33, 512, 200, {}),
+    ("bpad128", 100, 512, 256, {}),
+    ("bf16", 8, 256, 256, dict(dtype=torch.bfloat16)),
+]
+
+
+@pytest.mark.parametrize("fmt", [B200_FMT_F16, B200_FMT_INT8, B200_FMT_INT4], ids=["f16", "int8", "int4"])
+@pytest.mark.parametrize("case", GEMM_SMALL, ids=[c[0] for c in GEMM_SMALL])
+def test_gemm_vs_oracle(fmt, case):
+    """Tolerance (stated because the reference has no weight-only GEMM kernel to pin against):
+    |d| <= 1e-2*|y| + 1e-2 for FP16/INT8 weights, 2e-2 for INT4, vs fp32-accumulated X.W' with W' rounded to fp16."""
+    name, B, K, N, kw = case
+    _run(probe.gemm_case, f"{name}", fmt, B, K, N, **kw)
+
+
+@pytest.mark.parametrize("cfg", [("int4 Llama qkv B32", B200_FMT_INT4, 32, 4096, 6144),
+                                 ("int4 Llama w2 B32", B200_FMT_INT4, 32, 14336, 4096),
+                                 ("int4 Llama w13 B64", B200_FMT_INT4, 64, 4096, 28672),
+                                 ("int8 Llama o B32", B200_FMT_INT8, 32, 4096, 4096),
+                                 ("f16 lm_head slice B32", B200_FMT_F16, 32, 4096, 16032)], ids=lambda c: c[0])
+def test_gemm_full_size_vs_naive_gpu_kernel(cfg):
+    name, fmt, B, K, N = cfg
+    _run(probe.gemm_case, name, fmt, B, K, N, big=True)
+
+
+def test_gemm_is_linear_in_x():
+    """Size-independent property at a BASELINE shape: Y(a*x1 + x2) == a*Y(x1) + Y(x2) within fp16 rounding."""
+    dev = torch.device("cuda")
+    K, N, B = 4096, 4096, 32
+    qp, s, zs = probe.make_w4(K, N)
+    w = ops.pack_w4(torch.from_numpy(qp).to(dev), torch.from_numpy(s).to(dev), torch.from_numpy(zs).to(dev))
+    ws = ops.gemm_workspace(B, [(K, N)], dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    x1 = torch.randn(B, K, generator=g, device=dev).half()
+    x2 = torch.randn(B, K, generator=g, device=dev).half()
+    y1 = ops.wo_gemm(x1, w, ws).float()
+    y2 = ops.wo_gemm(x2, w, ws).float()
+    y3 = ops.wo_gemm((2 * x1 + x2), w, ws).float()
+    torch.testing.assert_close(y3, 2 * y1 + y2, rtol=2e-2, atol=2e-2 * float(y3.abs().mean()) + 2e-2)
+
+
+def test_glue_ops_and_indexing_vs_oracle():
+    _run(probe.glue_cases)

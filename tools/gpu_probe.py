@@ -156,7 +156,8 @@ def gemm_case(name, fmt, B, K, N, dtype=torch.float16, simple=False, onehot=Fals
                 ref = ops.ref_dequant_gemm(x, fmt, qd, sd, zd, 128, bias_t)
             elif fmt == B200_FMT_INT8:
                 q8 = rng.integers(-128, 128, (K, N)).astype(np.int8)
-                s = (np.abs(rng.standard_normal(N)) * 0.01 + 1e-3).astype(np.float32)
+                # realistic magnitude: W' ~ N(0, 0.02) like the loader's scale = amax/128 (device_impl.py:190)
+                s = (np.abs(rng.standard_normal(N)) * 2e-4 + 3e-4).astype(np.float32)
                 if simple:
                     s[:] = 1.0
                 qd, sd = torch.from_numpy(q8).to(dev), torch.from_numpy(s).to(dtype).to(dev)
