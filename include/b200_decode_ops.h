@@ -37,6 +37,11 @@ const char* b200_last_error(void);
 /* 0 if device `device` is sm_100 (B200) and the library's kernels can run there, else B200_EUNSUPPORTED. */
 int b200_device_check(int device);
 
+/* Library-wide switch: launch the kernels of the decode chain (norms, rope, attention, GEMMs) with programmatic dependent
+ * launch so each kernel's launch latency / prologue / weight prefetch overlaps its predecessor's tail. Every such kernel
+ * executes griddepcontrol.wait before touching dependent data, so results are unchanged. Default off. */
+int b200_set_pdl(int enable);
+
 /* Number of kernels this library has launched since load (all threads); used by bench.py for "gpu_launches". */
 uint64_t b200_launch_count(void);
 

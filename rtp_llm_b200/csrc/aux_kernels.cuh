@@ -110,6 +110,8 @@ __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t v) {
 template <typename T>
 __global__ void add_rmsnorm_kernel(const T* __restrict__ x, T* __restrict__ residual, const T* __restrict__ gamma,
                                    T* __restrict__ y, int hidden, float eps) {
+    pdl_launch_dependents();  // the next kernel (a GEMM) may start streaming its weights now
+    pdl_wait();               // our inputs come from the previous kernel
     extern __shared__ float s_row[];  // hidden floats
     __shared__ float s_red[32];
     const int row = blockIdx.x;
@@ -166,6 +168,8 @@ __global__ void add_rmsnorm_kernel(const T* __restrict__ x, T* __restrict__ resi
 // y[r][c] = silu(gate_up[r][c]) * gate_up[r][inter + c]   (activation_kernels.cu silu_and_mul semantics)
 template <typename T>
 __global__ void silu_and_mul_kernel(const T* __restrict__ gate_up, T* __restrict__ y, int rows, int inter) {
+    pdl_launch_dependents();
+    pdl_wait();
     const size_t total = (size_t)rows * inter / 2;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const size_t r = idx / (inter / 2), c2 = idx % (inter / 2);
@@ -185,6 +189,8 @@ __global__ void rope_append_kernel(const T* __restrict__ qkv, T* __restrict__ q_
                                    const int32_t* __restrict__ page_list, const int32_t* __restrict__ seq_lens,
                                    int head_num, int kv_head_num, int head_dim, int max_blocks, int tokens_per_block,
                                    float log2_base) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.x, h = blockIdx.y, i = threadIdx.x, half = head_dim / 2;
     const int pos = seq_lens[b];
     const T* src = qkv + ((size_t)b * (head_num + 2 * kv_head_num) + h) * head_dim;

@@ -53,6 +53,26 @@ int launched(const char* what) {
     return B200_OK;
 }
 
+std::atomic<int> g_pdl{0};
+
+// Launch through cudaLaunchKernelEx so a kernel can carry the programmatic-dependent-launch attribute: it may then be
+// scheduled while its predecessor drains (every kernel of the decode chain executes griddepcontrol.wait before it
+// touches dependent data, so this only overlaps launch latency, prologues and -- for the GEMM -- the weight prefetch).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
@@ -107,12 +127,15 @@ void attn_split(int units, int max_tiles, int* nsplit, int* tiles_per_split) {
     int best_c = max_tiles;
     double best = 1e30;
     const int sms = num_sms();
+    // Measured on B200 (profiles/r01_kernel_bench.txt): a CTA costs ~2.5 tiles of fixed time (launch, Q load, pipeline
+    // fill, merge) and two CTAs are resident per SM, so: fewest waves of 2*SMs slots, then the largest chunk.
+    const long slots = 2L * sms;
     for (int c = 1; c <= max_tiles; ++c) {
         const int ns = (max_tiles + c - 1) / c;
         if (ns > kAttnMaxSplit) continue;
         const long ctas = (long)units * ns;
-        const long per_sm = (ctas + sms - 1) / sms;
-        const double cost = (double)per_sm * (c + 0.6) + (ns > 1 ? 0.3 : 0.0);
+        const long waves = (ctas + slots - 1) / slots;
+        const double cost = (double)waves * (c + 2.5);
         if (cost < best - 1e-9 || (std::fabs(cost - best) <= 1e-9 && c > best_c)) {
             best = cost;
             best_c = c;
@@ -132,8 +155,10 @@ void attn_split(int units, int max_tiles, int* nsplit, int* tiles_per_split) {
 // ---- GEMM launch shape
 int gemm_bpad(int B) { return B <= 16 ? 16 : (B <= 32 ? 32 : (B <= 64 ? 64 : 128)); }
 void gemm_split(int n_tiles, int k_blocks, int* nsplit, int* kb_per_split) {
+    // Measured (profiles/r01_gemm_trace.txt): a CTA spends ~0.4 us per 128-deep k-block plus ~1.5-2 us of fixed time, two
+    // CTAs are resident per SM, and the split-K merge costs ~1 us. So: fill one wave of 2*SMs slots, then shorten chains.
     const int forced = env_int("B200_GEMM_SPLITK", 0);
-    const int sms = num_sms();
+    const long slots = 2L * num_sms();
     int best_s = 1;
     double best = 1e30;
     const int smax = k_blocks < 16 ? k_blocks : 16;
@@ -142,8 +167,8 @@ void gemm_split(int n_tiles, int k_blocks, int* nsplit, int* kb_per_split) {
         const int se = (k_blocks + kbp - 1) / kbp;
         if (se != s) continue;
         const long ctas = (long)n_tiles * se;
-        const long per_sm = (ctas + sms - 1) / sms;
-        const double cost = (double)per_sm * (kbp + 3.0) + (se > 1 ? 1.0 : 0.0);
+        const long waves = (ctas + slots - 1) / slots;
+        const double cost = (double)waves * (kbp + 4.0) + (se > 1 ? 2.0 : 0.0);
         if (cost < best - 1e-9) {
             best = cost;
             best_s = se;
@@ -156,10 +181,10 @@ void gemm_split(int n_tiles, int k_blocks, int* nsplit, int* kb_per_split) {
 }
 constexpr size_t kGemmSemBytes = 16384;
 
-template <int FMT, typename T, int BPAD>
-int launch_gemm(const CUtensorMap& xmap, const CUtensorMap& wmap, const GemmParams& p, int n_tiles, cudaStream_t st) {
-    auto kern = wo_gemm_kernel<FMT, T, BPAD>;
-    constexpr int smem = gemm_smem_bytes(FMT, BPAD);
+template <int FMT, typename T, int BPAD, int VAR>
+int launch_gemm_var(const CUtensorMap& xmap, const CUtensorMap& wmap, const GemmParams& p, int n_tiles, cudaStream_t st) {
+    auto kern = wo_gemm_kernel<FMT, T, BPAD, VAR>;
+    constexpr int smem = gemm_smem_bytes(FMT, BPAD, VAR);
     static bool configured = false;
     if (!configured) {
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -167,7 +192,7 @@ int launch_gemm(const CUtensorMap& xmap, const CUtensorMap& wmap, const GemmPara
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(n_tiles, p.nsplit, 1);
-    cfg.blockDim = dim3(kGemmThreads, 1, 1);
+    cfg.blockDim = dim3(gemm_threads(VAR), 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -177,6 +202,19 @@ int launch_gemm(const CUtensorMap& xmap, const CUtensorMap& wmap, const GemmPara
     cfg.numAttrs = p.use_pdl ? 1 : 0;
     CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, xmap, wmap, p));
     return launched("wo_gemm_kernel");
+}
+
+int gemm_variant() {
+    int v = env_int("B200_GEMM_VARIANT", 0);   // read per call: cheap, and lets one process compare variants
+    if (v < 0 || v >= kGemmVariants) v = 0;
+    return v;
+}
+template <int FMT, typename T, int BPAD>
+int launch_gemm(const CUtensorMap& xmap, const CUtensorMap& wmap, const GemmParams& p, int n_tiles, cudaStream_t st) {
+    switch (gemm_variant()) {
+        case 1: return launch_gemm_var<FMT, T, BPAD, 1>(xmap, wmap, p, n_tiles, st);
+        default: return launch_gemm_var<FMT, T, BPAD, 0>(xmap, wmap, p, n_tiles, st);
+    }
 }
 
 template <int FMT, typename T>
@@ -204,6 +242,11 @@ int dispatch_gemm_fmt(int fmt, int bpad, const CUtensorMap& xmap, const CUtensor
 extern "C" {
 
 const char* b200_last_error(void) { return g_err.c_str(); }
+
+int b200_set_pdl(int enable) {
+    g_pdl.store(enable ? 1 : 0);
+    return B200_OK;
+}
 
 uint64_t b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
@@ -324,14 +367,16 @@ int b200_paged_decode_attn(const void* q, int is_bf16, void* out, size_t head_nu
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
             configured[1] = true;
         }
-        paged_decode_attn_kernel<__nv_bfloat16><<<grid, kAttnThreads, kAttnSmemBytes, (cudaStream_t)stream>>>(map, p);
+        CUDA_CHECK(launch_ex(paged_decode_attn_kernel<__nv_bfloat16>, grid, dim3(kAttnThreads), kAttnSmemBytes,
+                             (cudaStream_t)stream, g_pdl.load() != 0, map, p));
     } else {
         if (!configured[0]) {
             CUDA_CHECK(cudaFuncSetAttribute(paged_decode_attn_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             kAttnSmemBytes));
             configured[0] = true;
         }
-        paged_decode_attn_kernel<__half><<<grid, kAttnThreads, kAttnSmemBytes, (cudaStream_t)stream>>>(map, p);
+        CUDA_CHECK(launch_ex(paged_decode_attn_kernel<__half>, grid, dim3(kAttnThreads), kAttnSmemBytes,
+                             (cudaStream_t)stream, g_pdl.load() != 0, map, p));
     }
     return launched("paged_decode_attn_kernel");
 }
@@ -405,7 +450,12 @@ int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const
     p.N = N;
     p.K = K;
     p.k_blocks = K / kGemmBK;
-    p.use_pdl = (flags & B200_GEMM_PDL) ? 1 : 0;
+    p.use_pdl = ((flags & B200_GEMM_PDL) || g_pdl.load()) ? 1 : 0;
+    p.dbg = env_int("B200_GEMM_DBG", 0);
+    {
+        const char* tr = getenv("B200_GEMM_TRACE_PTR");   // developer timeline buffer (device pointer, 8*64 int64)
+        p.trace = (tr && *tr) ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 0)) : nullptr;
+    }
     gemm_split(n_tiles, p.k_blocks, &p.nsplit, &p.kb_per_split);
     if (p.nsplit > 1) {
         const size_t tile_bytes = (size_t)n_tiles * bpad * kGemmTileN * sizeof(float);
@@ -452,12 +502,14 @@ int b200_add_rmsnorm(const void* x, void* residual, const void* gamma, void* y, 
     ARG_CHECK(hidden > 0 && hidden % 8 == 0 && hidden <= 12288, "add_rmsnorm: hidden=%d must be a multiple of 8, <= 12288", hidden);
     const int threads = hidden / 8 >= 512 ? 512 : (hidden / 8 >= 256 ? 256 : 128);
     const size_t smem = (size_t)hidden * sizeof(float);
+    const bool pdl = g_pdl.load() != 0;
     if (is_bf16)
-        add_rmsnorm_kernel<__nv_bfloat16><<<rows, threads, smem, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16*)x, (__nv_bfloat16*)residual, (const __nv_bfloat16*)gamma, (__nv_bfloat16*)y, hidden, eps);
+        CUDA_CHECK(launch_ex(add_rmsnorm_kernel<__nv_bfloat16>, dim3(rows), dim3(threads), smem, (cudaStream_t)stream, pdl,
+                             (const __nv_bfloat16*)x, (__nv_bfloat16*)residual, (const __nv_bfloat16*)gamma,
+                             (__nv_bfloat16*)y, hidden, eps));
     else
-        add_rmsnorm_kernel<__half><<<rows, threads, smem, (cudaStream_t)stream>>>((const __half*)x, (__half*)residual,
-                                                                                 (const __half*)gamma, (__half*)y, hidden, eps);
+        CUDA_CHECK(launch_ex(add_rmsnorm_kernel<__half>, dim3(rows), dim3(threads), smem, (cudaStream_t)stream, pdl,
+                             (const __half*)x, (__half*)residual, (const __half*)gamma, (__half*)y, hidden, eps));
     return launched("add_rmsnorm_kernel");
 }
 
@@ -469,11 +521,13 @@ int b200_silu_and_mul(const void* gate_up, void* y, int is_bf16, int rows, int i
     const int threads = 256;
     const size_t blocks = (total + threads - 1) / threads;
     const unsigned g = (unsigned)(blocks < 4 * 148 * 8 ? blocks : 4 * 148 * 8);
+    const bool pdl = g_pdl.load() != 0;
     if (is_bf16)
-        silu_and_mul_kernel<__nv_bfloat16><<<g, threads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)gate_up,
-                                                                                   (__nv_bfloat16*)y, rows, inter);
+        CUDA_CHECK(launch_ex(silu_and_mul_kernel<__nv_bfloat16>, dim3(g), dim3(threads), 0, (cudaStream_t)stream, pdl,
+                             (const __nv_bfloat16*)gate_up, (__nv_bfloat16*)y, rows, inter));
     else
-        silu_and_mul_kernel<__half><<<g, threads, 0, (cudaStream_t)stream>>>((const __half*)gate_up, (__half*)y, rows, inter);
+        CUDA_CHECK(launch_ex(silu_and_mul_kernel<__half>, dim3(g), dim3(threads), 0, (cudaStream_t)stream, pdl,
+                             (const __half*)gate_up, (__half*)y, rows, inter));
     return launched("silu_and_mul_kernel");
 }
 
@@ -486,14 +540,15 @@ int b200_rope_append(const void* qkv, void* q_out, void* kv_pool, const int32_t*
     ARG_CHECK(rope_base > 1.f, "rope_append: rope_base must be > 1");
     const dim3 grid(batch, head_num + 2 * kv_head_num);
     const float l2b = std::log2(rope_base);
+    const bool pdl = g_pdl.load() != 0;
     if (is_bf16)
-        rope_append_kernel<__nv_bfloat16><<<grid, head_dim / 2, 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16*)qkv, (__nv_bfloat16*)q_out, (__nv_bfloat16*)kv_pool, page_list, sequence_lengths,
-            head_num, kv_head_num, head_dim, max_blocks_per_seq, page_size, l2b);
+        CUDA_CHECK(launch_ex(rope_append_kernel<__nv_bfloat16>, grid, dim3(head_dim / 2), 0, (cudaStream_t)stream, pdl,
+                             (const __nv_bfloat16*)qkv, (__nv_bfloat16*)q_out, (__nv_bfloat16*)kv_pool, page_list,
+                             sequence_lengths, head_num, kv_head_num, head_dim, (int)max_blocks_per_seq, page_size, l2b));
     else
-        rope_append_kernel<__half><<<grid, head_dim / 2, 0, (cudaStream_t)stream>>>(
-            (const __half*)qkv, (__half*)q_out, (__half*)kv_pool, page_list, sequence_lengths, head_num, kv_head_num,
-            head_dim, max_blocks_per_seq, page_size, l2b);
+        CUDA_CHECK(launch_ex(rope_append_kernel<__half>, grid, dim3(head_dim / 2), 0, (cudaStream_t)stream, pdl,
+                             (const __half*)qkv, (__half*)q_out, (__half*)kv_pool, page_list, sequence_lengths, head_num,
+                             kv_head_num, head_dim, (int)max_blocks_per_seq, page_size, l2b));
     return launched("rope_append_kernel");
 }
 

@@ -56,6 +56,8 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.x, bh = blockIdx.y;
     const int b = bh / p.Hkv, kvh = bh % p.Hkv;
+    pdl_launch_dependents();   // let the o-projection GEMM start prefetching its weights
+    pdl_wait();                // q and the appended K/V come from the previous kernel
 
     const int len = p.seq_lens[b] + 1;
     const int ntiles = (len + kAttnTile - 1) / kAttnTile;

@@ -7,14 +7,14 @@
 //
 // B200 design (swap-AB, weights stationary on the MMA M side):
 //   * one CTA = 128 output features x a run of 128-deep k-blocks (split-K across blockIdx.y);
-//   * warp 0   : TMA producer. Weights were re-laid out at load time into per-(n-tile,k-block) contiguous blobs
+//   * TMA warp : producer. Weights were re-laid out at load time into per-(n-tile,k-block) contiguous blobs
 //                (packed nibbles + the group's scales and zero*scale), so one cp.async.bulk stages a whole block;
 //                the activation block [B x 128] comes through a 128B-swizzled tensor map (OOB rows zero-filled);
-//   * warps 2-9: dequantise IN REGISTERS (lop3 magic-number int->fp16, exact; hfma2 with the group scale / zero*scale)
+//   * dequant warps: dequantise IN REGISTERS (lop3 magic-number int->fp16, exact; hfma2 with the group scale / zero*scale)
 //                and store the fp16 operand straight INTO TENSOR MEMORY (tcgen05.st) -- the A operand of
-//   * warp 1   : one elected thread issues tcgen05.mma (M=128 features, N=batch pad, K=16) with A from TMEM and
+//   * MMA warp : one elected thread issues tcgen05.mma (M=128 features, N=batch pad, K=16) with A from TMEM and
 //                B (activations, K-major SW128) from shared memory, fp32 accumulators in TMEM;
-//   * epilogue : warps 2-9 read the accumulators (tcgen05.ld), split-K partials are merged by the last-arriving CTA
+//   * epilogue : the dequant warps read the accumulators (tcgen05.ld), split-K partials are merged by the last-arriving CTA
 //                (fixed order -> deterministic), bias / per-column scale applied, coalesced stores.
 //   The FP16-weight variant feeds A from shared memory (TMA tensor map, SW128) with the same pipeline.
 #pragma once
@@ -28,7 +28,6 @@ enum : int { kFmtF16 = 0, kFmtInt8 = 1, kFmtInt4 = 2 };
 
 constexpr int kGemmBK = 128;       // k elements per pipeline stage (= one INT4 quantisation group)
 constexpr int kGemmTileN = 128;    // output features per CTA (MMA M)
-constexpr int kGemmThreads = 320;  // warp0 TMA, warp1 MMA, warps 2..9 dequant + epilogue
 constexpr int kW4BlockBytes = 8192 + 256 + 256;
 constexpr int kW8BlockBytes = 16384;
 constexpr int kW16BlockBytes = 32768;
@@ -36,22 +35,45 @@ constexpr int kW16BlockBytes = 32768;
 __host__ __device__ constexpr int gemm_w_bytes(int fmt) {
     return fmt == kFmtInt4 ? kW4BlockBytes : (fmt == kFmtInt8 ? kW8BlockBytes : kW16BlockBytes);
 }
-__host__ __device__ constexpr int gemm_stage_bytes(int fmt, int bpad) {
-    return ((bpad * 256 + gemm_w_bytes(fmt)) + 1023) / 1024 * 1024;
+// Shared-memory rings.  The weight ring (HBM stream) and the activation ring (L2 hits) are SEPARATE: a weight stage is
+// released as soon as the dequant warps hold its nibbles in registers, so its lifetime is one TMA latency, not the
+// whole dequant -> TMEM -> MMA chain, and the bytes in flight per SM (Little's law: ~44 GB/s * latency) stay high.
+// Variants (env B200_GEMM_VARIANT): 0 = one group of 8 dequant warps; 1 = two groups of 8 that take alternate k-blocks
+// (two blocks in flight per CTA: the per-block chain wait -> LDS -> math -> TMEM store -> publish is latency-bound).
+constexpr int kGemmVariants = 2;
+__host__ __device__ constexpr int gemm_ndq_warps(int var) { return var == 1 ? 16 : 8; }
+__host__ __device__ constexpr int gemm_threads(int var) { return (gemm_ndq_warps(var) + 3) * 32; }
+__host__ __device__ constexpr int gemm_x_stage_bytes(int bpad) { return bpad * 256; }
+__host__ __device__ constexpr int gemm_x_stages(int bpad) { return bpad <= 32 ? 4 : 3; }
+constexpr int kGemmSmemMisc = 1024 /*align*/ + 1024 /*barriers*/;
+__host__ __device__ constexpr int gemm_w_stages_for(int fmt, int bpad, int budget) {
+    int n = (budget - kGemmSmemMisc - gemm_x_stages(bpad) * gemm_x_stage_bytes(bpad)) / gemm_w_bytes(fmt);
+    return n > 12 ? 12 : n;
 }
-__host__ __device__ constexpr int gemm_stages(int fmt, int bpad) {
-    // keep two CTAs per SM where the stage is small; >= 3 stages always
-    return fmt == kFmtF16 ? (bpad <= 64 ? 4 : 3) : (bpad <= 32 ? 6 : (bpad <= 64 ? 4 : 3));
+// two CTAs per SM when at least 4 weight stages fit in half an SM's shared memory
+__host__ __device__ constexpr int gemm_min_ctas(int fmt, int bpad, int var) {
+    (void)var;
+    return gemm_w_stages_for(fmt, bpad, 106 * 1024) >= 4 ? 2 : 1;
 }
-__host__ __device__ constexpr int gemm_a_stages(int bpad) { return bpad <= 64 ? 3 : 2; }
-__host__ __device__ constexpr int gemm_tmem_cols(int fmt, int bpad) {
-    int need = bpad + (fmt == kFmtF16 ? 0 : gemm_a_stages(bpad) * 64);
+__host__ __device__ constexpr int gemm_w_stages(int fmt, int bpad, int var) {
+    return gemm_min_ctas(fmt, bpad, var) == 2 ? gemm_w_stages_for(fmt, bpad, 106 * 1024)
+                                              : gemm_w_stages_for(fmt, bpad, 216 * 1024);
+}
+// Accumulator tiles the 8 k-steps of a block rotate over (the epilogue sums them). Measured (tools/gemm_trace.py): one
+// tile is enough -- back-to-back tcgen05.mma into the same accumulator pipeline fine; kept as a knob.
+__host__ __device__ constexpr int gemm_nacc(int bpad) { return bpad <= 64 ? 1 : 2; }
+__host__ __device__ constexpr int gemm_a_stages(int bpad, int var) {
+    (void)var;
+    return 3;
+}
+__host__ __device__ constexpr int gemm_tmem_cols(int fmt, int bpad, int var) {
+    int need = bpad * gemm_nacc(bpad) + (fmt == kFmtF16 ? 0 : gemm_a_stages(bpad, var) * 64);
     int c = 32;
     while (c < need) c *= 2;
     return c;
 }
-__host__ __device__ constexpr int gemm_smem_bytes(int fmt, int bpad) {
-    return gemm_stages(fmt, bpad) * gemm_stage_bytes(fmt, bpad) + 1024 /*align*/ + 512 /*barriers*/;
+__host__ __device__ constexpr int gemm_smem_bytes(int fmt, int bpad, int var) {
+    return gemm_x_stages(bpad) * gemm_x_stage_bytes(bpad) + gemm_w_stages(fmt, bpad, var) * gemm_w_bytes(fmt) + kGemmSmemMisc;
 }
 
 struct GemmParams {
@@ -65,6 +87,8 @@ struct GemmParams {
     float* ws;               // [nsplit][n_tiles][bpad][128] fp32 split-K partials
     int* sem;                // [n_tiles], zero on entry / exit
     int use_pdl;
+    long long* trace;        // developer timeline (tools/gemm_trace.py); null in production
+    int dbg;                 // developer experiments (env B200_GEMM_DBG): 1 no math, 2 no TMEM store, 4 no MMA; 0 in production
 };
 
 // ---- int4 -> fp16/bf16 pairs.  Nibble p of a word holds u = q_s + 8; p<4 <-> k = 2p, p>=4 <-> k = 2(p-4)+1, so each
@@ -159,48 +183,76 @@ struct Pair<__nv_bfloat16> {
     }
 };
 
-template <int FMT, typename T, int BPAD>
-__global__ void __launch_bounds__(kGemmThreads, (gemm_smem_bytes(FMT, BPAD) <= 110 * 1024) ? 2 : 1)
+// developer timeline: TRACE(slot, it) stores clock64() for CTA (0,0); slots: 0 w-issue, 1 x-issue, 2 dq wfull, 3 dq math done,
+// 4 dq aempty seen, 5 dq afull arrive (for it-1), 6 mma operands ready, 7 mma issued
+#define B200_TRACE(slot, it)                                                                     \
+    do {                                                                                         \
+        if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (it) < 64) p.trace[(slot) * 64 + (it)] = clock64(); \
+    } while (0)
+
+template <int FMT, typename T, int BPAD, int VAR>
+__global__ void __launch_bounds__(gemm_threads(VAR), gemm_min_ctas(FMT, BPAD, VAR))
 wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap w_map, const GemmParams p) {
-    constexpr int STAGES = gemm_stages(FMT, BPAD);
-    constexpr int STAGE_BYTES = gemm_stage_bytes(FMT, BPAD);
-    constexpr int X_BYTES = BPAD * 256;
+    constexpr int WS = gemm_w_stages(FMT, BPAD, VAR);      // weight ring depth
+    constexpr int XS = gemm_x_stages(BPAD);                // activation ring depth
+    constexpr int NDQ_WARPS = gemm_ndq_warps(VAR);
+    constexpr int NDQ_THREADS = NDQ_WARPS * 32;
+    constexpr int W_WTMA = NDQ_WARPS, W_XTMA = NDQ_WARPS + 1, W_MMA = NDQ_WARPS + 2;
+    constexpr int GROUPS = NDQ_WARPS / 8;                  // dequant warp groups; group g owns k-blocks it % GROUPS == g
+    constexpr int CPW = 2;                                 // 32-k chunks of a k-block handled by one warp
+    constexpr int X_BYTES = gemm_x_stage_bytes(BPAD);
     constexpr int W_BYTES = gemm_w_bytes(FMT);
-    constexpr int A_STAGES = gemm_a_stages(BPAD);
-    constexpr int TMEM_COLS = gemm_tmem_cols(FMT, BPAD);
-    constexpr int NDQ_WARPS = 8;
+    constexpr int A_STAGES = gemm_a_stages(BPAD, VAR);
+    constexpr int TMEM_COLS = gemm_tmem_cols(FMT, BPAD, VAR);
+    constexpr int NACC = gemm_nacc(BPAD);
     constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
     constexpr uint32_t IDESC = make_idesc_f16(kGemmTileN, BPAD, kBf16);
+    static_assert(WS >= 3, "weight ring too shallow");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // TMA landed (W + X)
-    uint64_t* empty_bar = full_bar + STAGES;                                       // smem stage free again
-    uint64_t* afull_bar = empty_bar + STAGES;                                      // TMEM A buffer written
-    uint64_t* aempty_bar = afull_bar + A_STAGES;                                   // TMEM A buffer consumed by the MMA
-    uint64_t* dfull_bar = aempty_bar + A_STAGES;                                   // accumulator complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dfull_bar + 1);
+    uint8_t* xring = smem;                                 // XS stages of [2 boxes][BPAD rows][128 B], SW128
+    uint8_t* wring = smem + XS * X_BYTES;                  // WS stages of one weight block each
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(wring + WS * W_BYTES);   // W_BYTES is a multiple of 512
+    uint64_t* wempty = wfull + WS;
+    uint64_t* xfull = wempty + WS;
+    uint64_t* xempty = xfull + XS;
+    uint64_t* afull = xempty + XS;                         // TMEM A buffer written
+    uint64_t* aempty = afull + A_STAGES;                   // TMEM A buffer consumed by the MMA
+    uint64_t* dfull = aempty + A_STAGES;                   // accumulator complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dfull + 1);
     int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x, split = blockIdx.y;
+    if (p.trace && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && blockIdx.y == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        const int o = blockIdx.x == 0 ? 0 : 4;
+        p.trace[8 * 64 + o + 0] = clock64();
+        p.trace[8 * 64 + o + 2] = (long long)gt;
+    }
     const int kb0 = split * p.kb_per_split;
     const int kb1 = min(kb0 + p.kb_per_split, p.k_blocks);
     const int nkb = kb1 - kb0;  // >= 1 by construction of the grid
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], FMT == kFmtF16 ? 1 : NDQ_WARPS + 1);
+        for (int s = 0; s < WS; ++s) {
+            mbar_init(&wfull[s], 1);
+            mbar_init(&wempty[s], FMT == kFmtF16 ? 1 : 8);
+        }
+        for (int s = 0; s < XS; ++s) {
+            mbar_init(&xfull[s], 1);
+            mbar_init(&xempty[s], 1);
         }
         for (int a = 0; a < A_STAGES; ++a) {
-            mbar_init(&afull_bar[a], NDQ_WARPS);
-            mbar_init(&aempty_bar[a], 1);
+            mbar_init(&afull[a], 8);
+            mbar_init(&aempty[a], 1);
         }
-        mbar_init(dfull_bar, 1);
+        mbar_init(dfull, 1);
         fence_mbar_init();
     }
-    if (warp == 1) {
+    if (warp == W_MMA) {
         tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
     }
@@ -208,143 +260,212 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_d = tmem_base;            // columns [0, BPAD): fp32 accumulators, lane = output feature
-    const uint32_t tmem_a = tmem_base + BPAD;     // columns [BPAD, BPAD + A_STAGES*64): fp16 A operand buffers
+    const uint32_t tmem_d = tmem_base;                // NACC accumulator tiles of BPAD fp32 columns, lane = output feature
+    const uint32_t tmem_a = tmem_base + NACC * BPAD;  // then A_STAGES buffers of 64 columns: the fp16 A operand
 
-    if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            tma_prefetch_desc(&x_map);
+    if (warp == W_WTMA) {
+        // ------------------------------------------------------------------ weight producer (HBM stream)
+        // Weights never depend on the previous kernel: under programmatic dependent launch this warp starts
+        // streaming at once; only the activation producer waits for the upstream grid.
+        if (elect_one()) {
             if (FMT == kFmtF16) tma_prefetch_desc(&w_map);
             const uint8_t* wsrc = p.w_blob + ((size_t)tile * p.k_blocks + kb0) * (size_t)W_BYTES;
-            // Weights never depend on the previous kernel: with programmatic dependent launch the first ring of
-            // weight blocks is requested BEFORE waiting on the upstream grid; only the activations wait.
-            const int pre = p.use_pdl ? min(nkb, STAGES) : 0;
-            for (int it = 0; it < pre; ++it) {
-                uint8_t* stage = smem + it * STAGE_BYTES;
-                mbar_arrive_expect_tx(&full_bar[it], X_BYTES + W_BYTES);
-                if (FMT == kFmtF16) {
-                    tma_load_2d(stage + X_BYTES, &w_map, (kb0 + it) * kGemmBK, tile * kGemmTileN, &full_bar[it]);
-                    tma_load_2d(stage + X_BYTES + 16384, &w_map, (kb0 + it) * kGemmBK + 64, tile * kGemmTileN,
-                                &full_bar[it]);
-                } else {
-                    tma_bulk_load(stage + X_BYTES, wsrc + (size_t)it * W_BYTES, W_BYTES, &full_bar[it]);
-                }
-            }
-            if (p.use_pdl) pdl_wait();
+            int s = 0;
+            uint32_t ph = 0;
             for (int it = 0; it < nkb; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                uint8_t* stage = smem + s * STAGE_BYTES;
-                const int k0 = (kb0 + it) * kGemmBK;
-                if (it >= pre) {
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[s], X_BYTES + W_BYTES);
-                    if (FMT == kFmtF16) {
-                        tma_load_2d(stage + X_BYTES, &w_map, k0, tile * kGemmTileN, &full_bar[s]);
-                        tma_load_2d(stage + X_BYTES + 16384, &w_map, k0 + 64, tile * kGemmTileN, &full_bar[s]);
-                    } else {
-                        tma_bulk_load(stage + X_BYTES, wsrc + (size_t)it * W_BYTES, W_BYTES, &full_bar[s]);
-                    }
+                uint8_t* stage = wring + s * W_BYTES;
+                mbar_wait(&wempty[s], ph ^ 1);
+                B200_TRACE(0, it);
+                mbar_arrive_expect_tx(&wfull[s], W_BYTES);
+                if (FMT == kFmtF16) {
+                    const int k0 = (kb0 + it) * kGemmBK;
+                    tma_load_2d(stage, &w_map, k0, tile * kGemmTileN, &wfull[s]);
+                    tma_load_2d(stage + 16384, &w_map, k0 + 64, tile * kGemmTileN, &wfull[s]);
+                } else {
+                    tma_bulk_load(stage, wsrc + (size_t)it * W_BYTES, W_BYTES, &wfull[s]);
                 }
-                tma_load_2d(stage, &x_map, k0, 0, &full_bar[s]);
-                tma_load_2d(stage + BPAD * 128, &x_map, k0 + 64, 0, &full_bar[s]);
+                if (++s == WS) {
+                    s = 0;
+                    ph ^= 1;
+                }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == W_XTMA) {
+        // ------------------------------------------------------------------ activation producer (L2 hits)
+        if (elect_one()) {
+            tma_prefetch_desc(&x_map);
+            if (p.use_pdl) pdl_wait();
+            int s = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < nkb; ++it) {
+                uint8_t* stage = xring + s * X_BYTES;
+                const int k0 = (kb0 + it) * kGemmBK;
+                mbar_wait(&xempty[s], ph ^ 1);
+                B200_TRACE(1, it);
+                mbar_arrive_expect_tx(&xfull[s], X_BYTES);
+                tma_load_2d(stage, &x_map, k0, 0, &xfull[s]);
+                tma_load_2d(stage + BPAD * 128, &x_map, k0 + 64, 0, &xfull[s]);
+                if (++s == XS) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+        }
+    } else if (warp == W_MMA) {
         // ------------------------------------------------------------------ MMA issuer (one elected thread)
+        // Warp-uniform control flow + elect.sync: ptxas then knows a single thread issues the tcgen05 instructions and
+        // moves their operands to uniform registers directly (with `if (lane == 0)` it emits an ELECT/R2UR/branch
+        // "waterfall" loop around EVERY UTCHMMA, ~100 cycles each -- measured with tools/gemm_trace.py).
         if (p.use_pdl && lane == 0) pdl_launch_dependents();
+        int sw = 0, sx = 0, a = 0;
+        uint32_t phw = 0, phx = 0, aph = 0;
         for (int it = 0; it < nkb; ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
-            const int a = it % A_STAGES;
-            const uint32_t aph = (it / A_STAGES) & 1;
-            mbar_wait(&full_bar[s], ph);
-            if (FMT != kFmtF16) mbar_wait(&afull_bar[a], aph);
+            mbar_wait(&xfull[sx], phx);
+            if (FMT == kFmtF16) mbar_wait(&wfull[sw], phw);
+            else mbar_wait(&afull[a], aph);
             tc_fence_after();
-            if (lane == 0) {
-                const uint32_t xs = smem_u32(smem + s * STAGE_BYTES);
+            if (elect_one()) {
+                B200_TRACE(6, it);
+                const uint32_t xs = smem_u32(xring + sx * X_BYTES);
+                const uint32_t wsm = smem_u32(wring + sw * W_BYTES);
 #pragma unroll
                 for (int j = 0; j < kGemmBK / 16; ++j) {
+                    if (p.dbg & 4) break;
                     const uint64_t bdesc = make_smem_desc_sw128(xs + (j >> 2) * (BPAD * 128) + (j & 3) * 32);
-                    const uint32_t acc = (it > 0 || j > 0) ? 1u : 0u;
+                    const uint32_t acc = (it > 0 || j >= NACC) ? 1u : 0u;
+                    const uint32_t dcol = tmem_d + (j % NACC) * BPAD;
                     if (FMT == kFmtF16) {
-                        const uint64_t adesc = make_smem_desc_sw128(xs + X_BYTES + (j >> 2) * 16384 + (j & 3) * 32);
-                        umma_ss_f16(tmem_d, adesc, bdesc, IDESC, acc);
+                        const uint64_t adesc = make_smem_desc_sw128(wsm + (j >> 2) * 16384 + (j & 3) * 32);
+                        umma_ss_f16(dcol, adesc, bdesc, IDESC, acc);
                     } else {
-                        umma_ts_f16(tmem_d, tmem_a + a * 64 + j * 8, bdesc, IDESC, acc);
+                        umma_ts_f16(dcol, tmem_a + a * 64 + j * 8, bdesc, IDESC, acc);
                     }
                 }
-                umma_commit(&empty_bar[s]);                      // X (and f16 W) of this stage consumed
-                if (FMT != kFmtF16) umma_commit(&aempty_bar[a]); // TMEM A buffer reusable
-                if (it == nkb - 1) umma_commit(dfull_bar);       // accumulator final
+                umma_commit(&xempty[sx]);                       // activation stage consumed
+                if (FMT == kFmtF16) umma_commit(&wempty[sw]);   // f16 weights are read by the MMA itself
+                else umma_commit(&aempty[a]);                   // TMEM A buffer reusable
+                if (it == nkb - 1) umma_commit(dfull);          // accumulator final
+                B200_TRACE(7, it);
             }
             __syncwarp();
+            if (++sx == XS) {
+                sx = 0;
+                phx ^= 1;
+            }
+            if (++sw == WS) {
+                sw = 0;
+                phw ^= 1;
+            }
+            if (++a == A_STAGES) {
+                a = 0;
+                aph ^= 1;
+            }
         }
     } else {
         // ------------------------------------------------------------------ dequant warps (TMEM A producers)
-        const int dq = warp - 2;          // 0..7
-        const int quarter = warp & 3;     // TMEM lane quarter this warp may touch
-        const int sub = dq >> 2;          // which half of the k-block / of the batch columns
+        const int quarter = warp & 3;     // TMEM lane quarter this warp may touch (hardware rule: warp id % 4)
+        const int grp = warp >> 3;        // dequant group
+        const int kc = (warp >> 2) & 1;   // which half (two 32-k chunks) of the k-block
         const int row = quarter * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         if (FMT != kFmtF16) {
-            for (int it = 0; it < nkb; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                const int a = it % A_STAGES;
-                const uint32_t aph = (it / A_STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
-                const uint8_t* wb = smem + s * STAGE_BYTES + X_BYTES;
-                uint32_t regs[2][16];
+            int s = grp % WS, a = grp % A_STAGES, a_prev = 0;
+            uint32_t ph = 0, aph = 0;
+            bool first = true;
+            for (int it = grp; it < nkb; it += GROUPS) {
+                mbar_wait(&wfull[s], ph);
+                if (threadIdx.x == 0) B200_TRACE(2, it);
+                const uint8_t* wb = wring + s * W_BYTES;
+                uint32_t regs[CPW][16];
                 if (FMT == kFmtInt4) {
                     const uint16_t* sc = reinterpret_cast<const uint16_t*>(wb + 8192);
                     const typename Pair<T>::type s2 = Pair<T>::bcast(sc[row]);
                     const typename Pair<T>::type zs2 = Pair<T>::bcast(sc[128 + row]);
+                    uint4 v[CPW];
 #pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
-                        const int c = sub * 2 + cc;  // 32-k chunk
-                        const uint4 v = *reinterpret_cast<const uint4*>(wb + c * 2048 + row * 16);
-                        Dequant4<T>::word(v.x, s2, zs2, &regs[cc][0]);
-                        Dequant4<T>::word(v.y, s2, zs2, &regs[cc][4]);
-                        Dequant4<T>::word(v.z, s2, zs2, &regs[cc][8]);
-                        Dequant4<T>::word(v.w, s2, zs2, &regs[cc][12]);
+                    for (int cc = 0; cc < CPW; ++cc)
+                        v[cc] = *reinterpret_cast<const uint4*>(wb + (kc * CPW + cc) * 2048 + row * 16);
+                    // the packed words are in registers: release the smem stage before doing the math
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&wempty[s]);
+#pragma unroll
+                    for (int cc = 0; cc < CPW; ++cc) {
+                        if (p.dbg & 1) {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) regs[cc][q] = (q & 1) ? v[cc].x ^ v[cc].w : v[cc].y ^ v[cc].z;
+                            continue;
+                        }
+                        Dequant4<T>::word(v[cc].x, s2, zs2, &regs[cc][0]);
+                        Dequant4<T>::word(v[cc].y, s2, zs2, &regs[cc][4]);
+                        Dequant4<T>::word(v[cc].z, s2, zs2, &regs[cc][8]);
+                        Dequant4<T>::word(v[cc].w, s2, zs2, &regs[cc][12]);
                     }
                 } else {
+                    uint4 v[CPW][2];
 #pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
+                    for (int cc = 0; cc < CPW; ++cc)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            v[cc][h] = *reinterpret_cast<const uint4*>(wb + ((kc * CPW + cc) * 2 + h) * 2048 + row * 16);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&wempty[s]);
+#pragma unroll
+                    for (int cc = 0; cc < CPW; ++cc)
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            const int c = sub * 4 + cc * 2 + h;  // 16-k chunk
-                            const uint4 v = *reinterpret_cast<const uint4*>(wb + c * 2048 + row * 16);
-                            Dequant8<T>::word(v.x, &regs[cc][h * 8 + 0]);
-                            Dequant8<T>::word(v.y, &regs[cc][h * 8 + 2]);
-                            Dequant8<T>::word(v.z, &regs[cc][h * 8 + 4]);
-                            Dequant8<T>::word(v.w, &regs[cc][h * 8 + 6]);
+                            Dequant8<T>::word(v[cc][h].x, &regs[cc][h * 8 + 0]);
+                            Dequant8<T>::word(v[cc][h].y, &regs[cc][h * 8 + 2]);
+                            Dequant8<T>::word(v[cc][h].z, &regs[cc][h * 8 + 4]);
+                            Dequant8<T>::word(v[cc][h].w, &regs[cc][h * 8 + 6]);
                         }
-                    }
                 }
-                // the packed weights are in registers: this warp is done with the smem stage
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[s]);
-                mbar_wait(&aempty_bar[a], aph ^ 1);
+                if (threadIdx.x == 0) B200_TRACE(3, it);
+                // software pipeline: the PREVIOUS block's TMEM stores had this block's math to complete; publish them now
+                if (!first) {
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&afull[a_prev]);
+                    if (threadIdx.x == 0) B200_TRACE(5, it);
+                }
+                first = false;
+                mbar_wait(&aempty[a], aph ^ 1);
+                if (threadIdx.x == 0) B200_TRACE(4, it);
                 tc_fence_after();
-                const uint32_t dst = tmem_a + lane_addr + a * 64 + sub * 32;
-                tmem_st_32x32b_x16(dst, regs[0]);
-                tmem_st_32x32b_x16(dst + 16, regs[1]);
+                const uint32_t dst = tmem_a + lane_addr + a * 64 + kc * CPW * 16;
+                if (p.dbg & 2) {
+                    if (regs[0][0] == 0x12345678u && regs[CPW - 1][15] == 0x9abcdef0u) s_flag[1] = 1;  // keep the math alive
+                } else {
+#pragma unroll
+                    for (int cc = 0; cc < CPW; ++cc) tmem_st_32x32b_x16(dst + cc * 16, regs[cc]);
+                }
+                a_prev = a;
+                s += GROUPS;
+                if (s >= WS) {
+                    s -= WS;
+                    ph ^= 1;
+                }
+                a += GROUPS;
+                if (a >= A_STAGES) {
+                    a -= A_STAGES;
+                    aph ^= 1;
+                }
+            }
+            if (!first) {
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&afull_bar[a]);
+                if (lane == 0) mbar_arrive(&afull[a_prev]);
             }
         }
 
         // ------------------------------------------------------------------ epilogue
-        mbar_wait(dfull_bar, 0);
+        mbar_wait(dfull, 0);
         tc_fence_after();
-        constexpr int COLS_PER_SUB = BPAD >= 32 ? BPAD / 2 : BPAD;  // BPAD=16: sub 0 takes all 16 columns
-        const bool active = (BPAD >= 32) || sub == 0;
-        const int col0 = (BPAD >= 32) ? sub * COLS_PER_SUB : 0;
+        // warps with the same lane quarter share the batch columns in slices of 16
+        constexpr int SLICES = BPAD / 16;                   // 16-column slices of the accumulator
+        constexpr int KCS = NDQ_WARPS / 4;                  // warps per lane quarter
+        const int kce = warp >> 2;                          // this warp's index among them
         const int n = tile * kGemmTileN + row;
         const bool n_ok = n < p.N;
         const int n_tiles = gridDim.x;
@@ -354,64 +475,85 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
             if (FMT == kFmtInt8) cscale = to_f32<T>(reinterpret_cast<const T*>(p.col_scale)[n]);
             if (p.bias) bias = to_f32<T>(reinterpret_cast<const T*>(p.bias)[n]);
         }
+        // 16 batch columns of this thread's feature row, summed over the NACC accumulator tiles
+        auto load_acc = [&](int sl, float (&v)[16]) {
+            uint32_t r[NACC][16];
+#pragma unroll
+            for (int q = 0; q < NACC; ++q) tmem_ld_32x32b_x16(tmem_d + lane_addr + q * BPAD + sl * 16, r[q]);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float a = __uint_as_float(r[0][j]);
+#pragma unroll
+                for (int q = 1; q < NACC; ++q) a += __uint_as_float(r[q][j]);
+                v[j] = a;
+            }
+        };
         if (p.nsplit == 1) {
-            if (active) {
+            for (int sl = kce; sl < SLICES; sl += KCS) {
+                float v[16];
+                load_acc(sl, v);
 #pragma unroll
-                for (int cb = 0; cb < COLS_PER_SUB; cb += 16) {
-                    uint32_t v[16];
-                    tmem_ld_32x32b_x16(tmem_d + lane_addr + col0 + cb, v);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int b = col0 + cb + j;
-                        if (n_ok && b < p.B) yp[(size_t)b * p.N + n] = from_f32<T>(fmaf(__uint_as_float(v[j]), cscale, bias));
-                    }
+                for (int j = 0; j < 16; ++j) {
+                    const int b = sl * 16 + j;
+                    if (n_ok && b < p.B) yp[(size_t)b * p.N + n] = from_f32<T>(fmaf(v[j], cscale, bias));
                 }
             }
         } else {
             // write the fp32 partial tile [bpad][128] (coalesced along n), then the last CTA of this n-tile reduces
             float* wsp = p.ws + ((size_t)split * n_tiles + tile) * (size_t)(BPAD * kGemmTileN);
-            if (active) {
+            for (int sl = kce; sl < SLICES; sl += KCS) {
+                float v[16];
+                load_acc(sl, v);
 #pragma unroll
-                for (int cb = 0; cb < COLS_PER_SUB; cb += 16) {
-                    uint32_t v[16];
-                    tmem_ld_32x32b_x16(tmem_d + lane_addr + col0 + cb, v);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int b = col0 + cb + j;
-                        if (b < p.B) __stcg(&wsp[(size_t)b * kGemmTileN + row], __uint_as_float(v[j]));
-                    }
+                for (int j = 0; j < 16; ++j) {
+                    const int b = sl * 16 + j;
+                    if (b < p.B) __stcg(&wsp[(size_t)b * kGemmTileN + row], v[j]);
                 }
             }
             __threadfence();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (threadIdx.x == 64) {
+            asm volatile("bar.sync 1, %0;" ::"n"(NDQ_THREADS) : "memory");
+            if (threadIdx.x == 0) {
                 const int prev = atomicAdd(&p.sem[tile], 1);
                 *s_flag = (prev == p.nsplit - 1);
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(NDQ_THREADS) : "memory");
             if (*s_flag) {
                 __threadfence();
-                if (active) {
-                    for (int cb = 0; cb < COLS_PER_SUB; ++cb) {
-                        const int b = col0 + cb;
-                        if (b >= p.B) break;
-                        float acc = 0.f;
-                        for (int sp = 0; sp < p.nsplit; ++sp)
-                            acc += __ldcg(&p.ws[((size_t)sp * n_tiles + tile) * (size_t)(BPAD * kGemmTileN) +
-                                                (size_t)b * kGemmTileN + row]);
-                        if (n_ok) yp[(size_t)b * p.N + n] = from_f32<T>(fmaf(acc, cscale, bias));
+                for (int sl = kce; sl < SLICES; sl += KCS) {
+                    // all loads of a slice are issued before the first use (the partials sit in L2)
+                    float acc[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+                    for (int sp = 0; sp < p.nsplit; ++sp) {
+                        const float* src = p.ws + ((size_t)sp * n_tiles + tile) * (size_t)(BPAD * kGemmTileN) + row;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int b = sl * 16 + j;
+                            if (b < p.B) acc[j] += __ldcg(src + (size_t)b * kGemmTileN);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int b = sl * 16 + j;
+                        if (n_ok && b < p.B) yp[(size_t)b * p.N + n] = from_f32<T>(fmaf(acc[j], cscale, bias));
                     }
                 }
-                if (threadIdx.x == 64) p.sem[tile] = 0;
+                if (threadIdx.x == 0) p.sem[tile] = 0;
             }
         }
         tc_fence_before();
     }
 
     __syncthreads();
-    if (warp == 1) {
+    if (p.trace && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && blockIdx.y == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        const int o = blockIdx.x == 0 ? 0 : 4;
+        p.trace[8 * 64 + o + 1] = clock64();
+        p.trace[8 * 64 + o + 3] = (long long)gt;
+    }
+    if (warp == W_MMA) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }

@@ -157,6 +157,7 @@ class DecodeStep:
         shapes = [(H, qkv_n), (self.Hq * self.D, H), (H, 2 * self.inter), (self.inter, H), (H, self.vocab)]
         self.gemm_ws = ops.gemm_workspace(batch, shapes, device)
         self.attn_ws = ops.attn_workspace(batch, self.Hq, self.Hkv, ctx, device)
+        ops.set_pdl(pdl)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.upload_inputs()
         torch.cuda.synchronize(device)

@@ -36,6 +36,11 @@ def device_check(device: int = 0) -> None:
     check(_lib.load().b200_device_check(device), "b200_device_check")
 
 
+def set_pdl(enable: bool) -> None:
+    """Programmatic dependent launch for the whole decode chain (see include/b200_decode_ops.h)."""
+    check(_lib.load().b200_set_pdl(1 if enable else 0), "b200_set_pdl")
+
+
 def launch_count() -> int:
     return int(_lib.load().b200_launch_count())
 

@@ -48,9 +48,9 @@ def oracle_step(model: DecodeStep, kv_before):
     return orc.from_bits(logits, False)
 
 
-def check_tiny_step(dev, quant="int4", batch=3, ctx=40, graph=False) -> float:
+def check_tiny_step(dev, quant="int4", batch=3, ctx=40, graph=False, pdl=False) -> float:
     cfg = dataclasses.replace(TINY, quant=quant)
-    model = DecodeStep(cfg, batch, ctx, dev, keep_reference=True, ragged=True, seed=1)
+    model = DecodeStep(cfg, batch, ctx, dev, keep_reference=True, ragged=True, seed=1, pdl=pdl)
     kv_before = [_bits(L["kv"]) for L in model.layers]
     if graph:
         for L, kb in zip(model.layers, kv_before):   # capture() runs the step (appends K/V): the append is idempotent
@@ -60,6 +60,9 @@ def check_tiny_step(dev, quant="int4", batch=3, ctx=40, graph=False) -> float:
     else:
         model.step()
     torch.cuda.synchronize(dev)
+    if pdl:
+        from rtp_llm_b200 import ops
+        ops.set_pdl(False)
     got = model.logits.float().cpu().numpy()
     exp = oracle_step(model, kv_before)
     scale = float(np.sqrt((exp ** 2).mean()))

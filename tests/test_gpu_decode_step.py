@@ -13,3 +13,8 @@ def test_tiny_decode_step_matches_oracle(quant):
 
 def test_tiny_decode_step_under_cuda_graph():
     check_tiny_step(torch.device("cuda:0"), quant="int4", batch=5, ctx=70, graph=True)
+
+
+def test_tiny_decode_step_with_programmatic_dependent_launch():
+    check_tiny_step(torch.device("cuda:0"), quant="int4", batch=5, ctx=70, graph=True, pdl=True)
+    check_tiny_step(torch.device("cuda:0"), quant="int8", batch=3, ctx=40, graph=False, pdl=True)

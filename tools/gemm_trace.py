@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Developer tool: per-k-block timeline (clock64) of CTA (0,0) of the weight-only GEMM."""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from rtp_llm_b200 import ops
+from rtp_llm_b200._lib import B200_FMT_INT4, B200_FMT_INT8
+
+dev = torch.device("cuda:0")
+fmt = {"int4": B200_FMT_INT4, "int8": B200_FMT_INT8}[sys.argv[1] if len(sys.argv) > 1 else "int4"]
+B, K, N = 32, 4096, 28672
+if fmt == B200_FMT_INT4:
+    qp = torch.randint(0, 256, (K, N // 2), device=dev, dtype=torch.uint8)
+    s = (torch.randn(K // 128, N, device=dev).abs() * 0.01 + 1e-3).half()
+    w = ops.pack_w4(qp, s, s)
+else:
+    w = ops.pack_w8(torch.randint(-128, 128, (K, N), device=dev, dtype=torch.int8), torch.ones(N, device=dev).half())
+x = torch.randn(B, K, device=dev).half()
+ws = ops.gemm_workspace(B, [(K, N)], dev)
+for _ in range(3):
+    ops.wo_gemm(x, w, ws)
+trace = torch.zeros(8 * 64 + 8, dtype=torch.int64, device=dev)
+os.environ["B200_GEMM_TRACE_PTR"] = str(trace.data_ptr())
+ops.wo_gemm(x, w, ws)
+torch.cuda.synchronize()
+os.environ.pop("B200_GEMM_TRACE_PTR")
+ex = trace.cpu()[8 * 64:]
+t = trace.cpu()[: 8 * 64].view(8, 64)
+t0 = int(t[0, 0])
+names = ["w_issue", "x_issue", "dq_wfull", "dq_math", "dq_aempty", "dq_afullarr", "mma_ready", "mma_issued"]
+print("it  " + " ".join(f"{n:>11s}" for n in names))
+for it in range(32):
+    print(f"{it:2d}  " + " ".join(f"{int(t[r, it]) - t0 if int(t[r, it]) else -1:11d}" for r in range(8)))
+
+for nm, o in (("first CTA", 0), ("last CTA", 4)):
+    cyc, ns = int(ex[o + 1] - ex[o + 0]), int(ex[o + 3] - ex[o + 2])
+    print(f"{nm}: {cyc} cycles in {ns} ns -> {cyc / max(ns, 1):.3f} GHz; start offset vs first CTA {int(ex[o + 2] - ex[2])} ns; entry->first W issue {t0 - int(ex[0])} cyc")
+print("first CTA: last mma issued -> kernel end", int(ex[1]) - int(t[7, 31]), "cycles")

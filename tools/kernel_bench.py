@@ -21,17 +21,33 @@ except Exception:  # noqa: BLE001
     pass
 
 
-def timeit(fn, n_rot, iters=40, warm=5):
-    for i in range(warm):
+def timeit(fn, n_rot, iters=20, warm=3):
+    """Average device time per call with the calls replayed from a CUDA graph (no CPU launch overhead in the number)."""
+    calls = max(n_rot, 8)
+    for i in range(calls):
         fn(i % n_rot)
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for i in range(calls):
+            fn(i % n_rot)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(calls):
+            fn(i % n_rot)
+    for _ in range(warm):
+        g.replay()
     torch.cuda.synchronize()
     st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     st.record()
-    for i in range(iters):
-        fn(i % n_rot)
+    for _ in range(iters):
+        g.replay()
     en.record()
     torch.cuda.synchronize()
-    return st.elapsed_time(en) / iters * 1e3  # us
+    return st.elapsed_time(en) / (iters * calls) * 1e3  # us
 
 
 def bench_attn(B, Hq, Hkv, S, T=64, nrot=3, env=None):
@@ -85,6 +101,13 @@ def bench_gemm(fmt, B, K, N, env=None, pdl=False):
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["attn", "gemm"]
+    if which[0] == "one_gemm":     # one_gemm fmt B K N  (for ncu)
+        f = {"f16": B200_FMT_F16, "int8": B200_FMT_INT8, "int4": B200_FMT_INT4}[which[1]]
+        bench_gemm(f, int(which[2]), int(which[3]), int(which[4]))
+        sys.exit(0)
+    if which[0] == "one_attn":     # one_attn B Hq Hkv S
+        bench_attn(int(which[1]), int(which[2]), int(which[3]), int(which[4]))
+        sys.exit(0)
     print(torch.cuda.get_device_name(0), "peak", PEAK)
     if "attn" in which:
         bench_attn(32, 32, 8, 2048)
@@ -94,18 +117,13 @@ if __name__ == "__main__":
         bench_attn(64, 32, 8, 4096)
         bench_attn(16, 8, 1, 8192)
     if "gemm" in which:
-        for B in (1, 32, 64):
-            bench_gemm(B200_FMT_INT4, B, 4096, 6144)
-            bench_gemm(B200_FMT_INT4, B, 4096, 4096)
-            bench_gemm(B200_FMT_INT4, B, 4096, 28672)
-            bench_gemm(B200_FMT_INT4, B, 14336, 4096)
-        for s in (1, 2, 4, 8):
-            bench_gemm(B200_FMT_INT4, 32, 4096, 6144, env={"B200_GEMM_SPLITK": s})
-            bench_gemm(B200_FMT_INT4, 32, 14336, 4096, env={"B200_GEMM_SPLITK": s})
-        for s in (1, 2, 3, 4):
-            bench_gemm(B200_FMT_INT4, 32, 4096, 28672, env={"B200_GEMM_SPLITK": s})
-        bench_gemm(B200_FMT_INT4, 32, 4096, 28672, pdl=True)
-        bench_gemm(B200_FMT_INT8, 32, 4096, 28672)
-        bench_gemm(B200_FMT_INT8, 32, 14336, 4096)
-        bench_gemm(B200_FMT_F16, 32, 4096, 28672)
-        bench_gemm(B200_FMT_F16, 32, 4096, 128256)
+        for var in (0, 1):
+            print(f"--- GEMM variant {var}")
+            os.environ["B200_GEMM_VARIANT"] = str(var)
+            bench_gemm(B200_FMT_INT4, 32, 4096, 28672)
+            for dbg in (1, 2, 4, 3, 5, 6, 7):
+                bench_gemm(B200_FMT_INT4, 32, 4096, 28672, env={"B200_GEMM_DBG": dbg})
+            bench_gemm(B200_FMT_INT8, 32, 4096, 28672)
+            for dbg in (2, 4, 6):
+                bench_gemm(B200_FMT_INT8, 32, 4096, 28672, env={"B200_GEMM_DBG": dbg})
+        os.environ["B200_GEMM_VARIANT"] = "0"
