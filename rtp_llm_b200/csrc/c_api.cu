@@ -163,6 +163,7 @@ void gemm_split(int n_tiles, int k_blocks, int* nsplit, int* kb_per_split) {
     double best = 1e30;
     const int smax = k_blocks < 16 ? k_blocks : 16;
     for (int s = 1; s <= smax; ++s) {
+        if (s > 1 && n_tiles >= slots) break;   // already more than a wave of tiles: splitting only adds merge traffic
         const int kbp = (k_blocks + s - 1) / s;
         const int se = (k_blocks + kbp - 1) / kbp;
         if (se != s) continue;

@@ -225,12 +225,15 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x, split = blockIdx.y;
-    if (p.trace && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && blockIdx.y == 0) {
+    if (p.trace && threadIdx.x == 0) {
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-        const int o = blockIdx.x == 0 ? 0 : 4;
-        p.trace[8 * 64 + o + 0] = clock64();
-        p.trace[8 * 64 + o + 2] = (long long)gt;
+        atomicMin(reinterpret_cast<unsigned long long*>(&p.trace[8 * 64 + 14]), gt);   // earliest CTA start (ns)
+        if ((blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && blockIdx.y == 0) {
+            const int o = blockIdx.x == 0 ? 0 : 4;
+            p.trace[8 * 64 + o + 0] = clock64();
+            p.trace[8 * 64 + o + 2] = (long long)gt;
+        }
     }
     const int kb0 = split * p.kb_per_split;
     const int kb1 = min(kb0 + p.kb_per_split, p.k_blocks);
@@ -460,8 +463,14 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
         }
 
         // ------------------------------------------------------------------ epilogue
+#define B200_TRACE_E(i)                                                                                          \
+    do {                                                                                                         \
+        if (p.trace && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) p.trace[8 * 64 + 8 + (i)] = clock64(); \
+    } while (0)
+        B200_TRACE_E(0);
         mbar_wait(dfull, 0);
         tc_fence_after();
+        B200_TRACE_E(1);
         // warps with the same lane quarter share the batch columns in slices of 16
         constexpr int SLICES = BPAD / 16;                   // 16-column slices of the accumulator
         constexpr int KCS = NDQ_WARPS / 4;                  // warps per lane quarter
@@ -511,13 +520,16 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
                     if (b < p.B) __stcg(&wsp[(size_t)b * kGemmTileN + row], v[j]);
                 }
             }
+            B200_TRACE_E(2);
             __threadfence();
             asm volatile("bar.sync 1, %0;" ::"n"(NDQ_THREADS) : "memory");
+            B200_TRACE_E(3);
             if (threadIdx.x == 0) {
                 const int prev = atomicAdd(&p.sem[tile], 1);
                 *s_flag = (prev == p.nsplit - 1);
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NDQ_THREADS) : "memory");
+            B200_TRACE_E(4);
             if (*s_flag) {
                 __threadfence();
                 for (int sl = kce; sl < SLICES; sl += KCS) {
@@ -542,16 +554,20 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
                 if (threadIdx.x == 0) p.sem[tile] = 0;
             }
         }
+        B200_TRACE_E(5);
         tc_fence_before();
     }
 
     __syncthreads();
-    if (p.trace && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && blockIdx.y == 0) {
+    if (p.trace && threadIdx.x == 0) {
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-        const int o = blockIdx.x == 0 ? 0 : 4;
-        p.trace[8 * 64 + o + 1] = clock64();
-        p.trace[8 * 64 + o + 3] = (long long)gt;
+        atomicMax(reinterpret_cast<unsigned long long*>(&p.trace[8 * 64 + 15]), gt);   // latest CTA end (ns)
+        if ((blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && blockIdx.y == 0) {
+            const int o = blockIdx.x == 0 ? 0 : 4;
+            p.trace[8 * 64 + o + 1] = clock64();
+            p.trace[8 * 64 + o + 3] = (long long)gt;
+        }
     }
     if (warp == W_MMA) {
         tc_fence_after();

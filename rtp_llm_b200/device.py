@@ -1,0 +1,92 @@
+"""Host-side mirror of the loader's device hooks: DeviceBase.{apply_int8, preprocess_groupwise_weight_params,
+preprocess_weights_for_mixed_gemm} (/root/reference/rtp_llm/device/device_base.py:56-90), instance stored in
+LoadConfig.exported_device (model_loader/loader.py:79).
+
+The unpack / quantise arithmetic restates device_impl.py:148-300 in torch (bit-exact against the reference's code on the
+golden fixtures, tests/test_host_logic.py); only the final re-layout differs: instead of the FT sm80 interleave
+(device_impl.py:392-479) weights go into the TMA-friendly blobs of include/b200_decode_ops.h."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def unpack_int32_into_int16(w_packed: torch.Tensor) -> torch.Tensor:
+    """device_impl.py:148-161, 4-bit branch: int32 words -> nibbles along the last axis, low nibble first."""
+    b = w_packed.contiguous().view(torch.uint8)
+    out = torch.empty(b.shape[0], b.shape[1] * 2, dtype=torch.int16, device=b.device)
+    out[:, ::2] = (b % 16).to(torch.int16)
+    out[:, 1::2] = (b // 16).to(torch.int16)
+    return out
+
+
+def reverse_awq_order(t: torch.Tensor) -> torch.Tensor:
+    """device_impl.py:163-171."""
+    return t.reshape(-1, 2, 4).transpose(2, 1).reshape(t.shape)
+
+
+def pack_int8_tensor_to_packed_int4(t: torch.Tensor) -> torch.Tensor:
+    """device_impl.py:204-209: two's-complement nibbles, low nibble = even column."""
+    u = (t.to(torch.int16) & 0xF).to(torch.uint8)
+    return (u[:, 1::2] * 16 + u[:, ::2]).contiguous()
+
+
+class B200Impl:
+    """Drop-in for CudaImpl's weight hooks. Returned `kernel` tensors carry the packed weight as `._b200_packed`."""
+
+    def __init__(self, device="cuda", act_dtype=torch.float16):
+        self.device, self.act_dtype = torch.device(device), act_dtype
+
+    # -- device_impl.py:183-202 / 215-222
+    def symmetric_quantize_last_axis_of_batched_matrix(self, weight: torch.Tensor, quant_mode=torch.int8):
+        amax = torch.clamp(weight.abs().max(dim=0)[0], min=1e-8)
+        scale = amax / 128.0
+        q = torch.clamp((weight / scale).round(), -128, 127).char()
+        return q, scale
+
+    def apply_int8(self, tensor: torch.Tensor, device: str = "cuda"):
+        shape = tensor.shape
+        q, scale = self.symmetric_quantize_last_axis_of_batched_matrix(tensor.reshape(shape[0], -1).float())
+        packed = ops.pack_w8(q.to(self.device).contiguous(), scale.to(self.act_dtype).to(self.device))
+        kernel = packed.data
+        kernel._b200_packed = packed
+        return kernel, scale.to(self.device)
+
+    # -- device_impl.py:242-300
+    def unpack_groupwise(self, qweight_int32, qzeros_int32, scales_fp16, gptq: bool, awq: bool, weight_bits: int = 4):
+        """Returns the loader's UN-permuted tensors (q_packed uint8 [K,N/2], zeros_x_scales fp16, scales fp16)."""
+        assert weight_bits == 4, "INT8 group-wise checkpoints are outside the built scope"
+        qweight = qweight_int32.reshape(qweight_int32.shape[0], -1)
+        qzeros = qzeros_int32.reshape(qzeros_int32.shape[0], -1)
+        scales = scales_fp16.reshape(scales_fp16.shape[0], -1)
+        if awq:
+            q = reverse_awq_order(unpack_int32_into_int16(qweight) - 8)
+        elif gptq:
+            q = (unpack_int32_into_int16(qweight.T.contiguous()).T.contiguous() - 8)
+        else:
+            raise ValueError("need gptq or awq")
+        q_packed = pack_int8_tensor_to_packed_int4(q.to(torch.int8))
+        z = unpack_int32_into_int16(qzeros)
+        if awq:
+            z = reverse_awq_order(z)
+        zeros_x_scales = ((-z + 8 - (1 if gptq else 0)) * scales).half()
+        return q_packed, zeros_x_scales, scales
+
+    def preprocess_groupwise_weight_params(self, qweight_int32, qzeros_int32, scales_fp16, device: str, gptq: bool,
+                                           awq: bool, weight_bits: int):
+        q_packed, zs, scales = self.unpack_groupwise(qweight_int32, qzeros_int32, scales_fp16, gptq, awq, weight_bits)
+        kernel = self.preprocess_weights_for_mixed_gemm(q_packed, torch.quint4x2, scales=scales, zeros_x_scales=zs)
+        return kernel, zs.to(self.device), scales.to(self.device)
+
+    # -- replaces device_impl.py:392-479
+    def preprocess_weights_for_mixed_gemm(self, tensor: torch.Tensor, quant_mode, arch: str = "", scales=None,
+                                          zeros_x_scales=None):
+        if quant_mode == torch.int8:
+            raise ValueError("INT8 per-column weights are packed by apply_int8 (the scale rides along)")
+        assert scales is not None and zeros_x_scales is not None, "the b200 INT4 blob carries scales and zero*scale"
+        packed = ops.pack_w4(tensor.to(self.device).contiguous(), scales.to(self.act_dtype).to(self.device).contiguous(),
+                             zeros_x_scales.to(self.act_dtype).to(self.device).contiguous())
+        kernel = packed.data
+        kernel._b200_packed = packed
+        return kernel

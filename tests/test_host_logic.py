@@ -1,0 +1,79 @@
+"""CPU tests of the host-side logic above the C ABI: the torch restatement of the loader's unpack code in
+rtp_llm_b200/device.py is bit-exact against the golden vectors produced by the reference's own code, and the
+strategy / impl classes expose the reference's method surface."""
+import inspect
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from rtp_llm_b200 import attention, device, linear
+
+
+@pytest.mark.parametrize("fmt", ["gptq", "awq"])
+def test_unpack_groupwise_torch_matches_reference(golden_dir, fmt):
+    g = np.load(os.path.join(golden_dir, f"quant_unpack_{fmt}.npz"))
+    impl = device.B200Impl(device="cpu")
+    qp, zs, sc = impl.unpack_groupwise(torch.from_numpy(g["qweight"]), torch.from_numpy(g["qzeros"]),
+                                       torch.from_numpy(g["scales"]), gptq=fmt == "gptq", awq=fmt == "awq")
+    assert np.array_equal(qp.numpy(), g["q_packed"])
+    assert np.array_equal(zs.numpy().view(np.uint16), g["zeros_x_scales"].view(np.uint16))
+    assert np.array_equal(sc.numpy().view(np.uint16), g["scales_out"].view(np.uint16))
+
+
+def test_int8_quantiser_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "quant_int8.npz"))
+    q, s = device.B200Impl(device="cpu").symmetric_quantize_last_axis_of_batched_matrix(torch.from_numpy(g["weight"]))
+    assert np.array_equal(q.numpy(), g["q"])
+    assert np.array_equal(s.numpy(), g["scale"])
+
+
+def test_interfaces_have_the_reference_surface():
+    # XQAAttnOp method set (XQAAttnOp.cc:158-176)
+    for m in ("support", "prepare", "update", "update_kv_cache_offset", "forward"):
+        assert callable(getattr(attention.B200DecodeAttnOp, m))
+    # FMHAImplBase strategy (fmha_impl_base.py:99-175)
+    sig = inspect.signature(attention.B200DecodeImpl.forward)
+    assert list(sig.parameters)[1:] == ["qkv", "kv_cache", "layer_idx"]
+    assert callable(attention.B200DecodeImpl.prepare_cuda_graph) and callable(attention.B200DecodeImpl.support)
+    assert list(inspect.signature(attention.B200DecodeImpl.__init__).parameters)[1:] == \
+        ["attn_configs", "attn_inputs", "parallelism_config"]
+    # LinearBase strategy (linear_base.py:25-49)
+    assert list(inspect.signature(linear.B200WeightOnlyLinear.can_handle).parameters) == \
+        ["quant_config", "weight", "weight_scales", "hw_kernel_config", "weight_scale_2", "input_scale"]
+    assert list(inspect.signature(linear.B200WeightOnlyLinear.__init__).parameters)[1:] == \
+        ["weight", "weight_scales", "input_scales", "bias", "quant_config", "weight_scale_2"]
+    # DeviceBase hooks (device_base.py:56-90)
+    for m in ("apply_int8", "preprocess_groupwise_weight_params", "preprocess_weights_for_mixed_gemm"):
+        assert callable(getattr(device.B200Impl, m))
+
+
+def test_strategy_selection_rules():
+    class Q:  # stands in for config/quant_config.py objects
+        def __init__(self, m):
+            self._m = m
+
+        def get_method(self):
+            return self._m
+    L = linear.B200WeightOnlyLinear
+    w8 = torch.zeros(4, 4, dtype=torch.int8)
+    assert L.can_handle(Q("awq"), w8, torch.ones(1, 4))
+    assert L.can_handle(Q("GPTQ"), w8, torch.ones(1, 4))
+    assert L.can_handle(Q("int8"), w8, torch.ones(4))
+    assert not L.can_handle(Q("fp8"), torch.zeros(4, 4, dtype=torch.float8_e4m3fn), torch.ones(4))
+    assert not L.can_handle(Q("awq"), w8, torch.ones(4), weight_scale_2=torch.ones(1))
+    assert L.can_handle(None, torch.zeros(4, 4, dtype=torch.float16), None)
+
+
+def test_attn_op_support_gate():
+    class C:
+        head_num, kv_head_num, size_per_head, tokens_per_block, kernel_tokens_per_block = 32, 8, 128, 64, 64
+        kv_cache_dtype = "BASE"
+
+    class I:
+        is_prefill = True
+    assert attention.B200DecodeAttnOp(C()).support(I()) is False          # decode only
+    C.size_per_head = 64
+    I.is_prefill = False
+    assert attention.B200DecodeAttnOp(C()).support(I()) is False          # head_dim 128 only
