@@ -154,16 +154,19 @@ void attn_split(int units, int max_tiles, int* nsplit, int* tiles_per_split) {
 
 // ---- GEMM launch shape
 int gemm_bpad(int B) { return B <= 16 ? 16 : (B <= 32 ? 32 : (B <= 64 ? 64 : 128)); }
-void gemm_split(int n_tiles, int k_blocks, int* nsplit, int* kb_per_split) {
+void gemm_split(int n_tiles, int k_blocks, int max_split, int* nsplit, int* kb_per_split) {
     // Measured (profiles/r01_gemm_trace.txt): a CTA spends ~0.4 us per 128-deep k-block plus ~1.5-2 us of fixed time, two
     // CTAs are resident per SM, and the split-K merge costs ~1 us. So: fill one wave of 2*SMs slots, then shorten chains.
     const int forced = env_int("B200_GEMM_SPLITK", 0);
     const long slots = 2L * num_sms();
     int best_s = 1;
     double best = 1e30;
-    const int smax = k_blocks < 16 ? k_blocks : 16;
+    const int smax = k_blocks < max_split ? k_blocks : max_split;
+    const bool cluster = max_split <= 8;   // cluster mode: the nsplit CTAs of a tile must be co-scheduled inside one GPC
     for (int s = 1; s <= smax; ++s) {
         if (s > 1 && n_tiles >= slots) break;   // already more than a wave of tiles: splitting only adds merge traffic
+        if (cluster && s > 1 && (s & (s - 1))) continue;                       // powers of two pack GPCs without strays
+        if (cluster && s > 1 && n_tiles > 8 * (32 / s)) continue;              // >= 16 SMs (32 slots) per GPC, 8 GPCs
         const int kbp = (k_blocks + s - 1) / s;
         const int se = (k_blocks + kbp - 1) / kbp;
         if (se != s) continue;
@@ -175,7 +178,7 @@ void gemm_split(int n_tiles, int k_blocks, int* nsplit, int* kb_per_split) {
             best_s = se;
         }
     }
-    if (forced > 0) best_s = forced < k_blocks ? forced : k_blocks;
+    if (forced > 0) best_s = forced < smax ? forced : smax;
     int kbp = (k_blocks + best_s - 1) / best_s;
     *kb_per_split = kbp;
     *nsplit = (k_blocks + kbp - 1) / kbp;
@@ -196,11 +199,22 @@ int launch_gemm_var(const CUtensorMap& xmap, const CUtensorMap& wmap, const Gemm
     cfg.blockDim = dim3(gemm_threads(VAR), 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (p.use_pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (p.nsplit > 1 && p.cluster_reduce) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1;
+        attr[na].val.clusterDim.y = (unsigned)p.nsplit;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = p.use_pdl ? 1 : 0;
+    cfg.numAttrs = na;
     CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, xmap, wmap, p));
     return launched("wo_gemm_kernel");
 }
@@ -422,7 +436,7 @@ size_t b200_wo_gemm_workspace_bytes(int max_batch, int N, int K) {
     if (max_batch <= 0 || N <= 0 || K <= 0 || K % kGemmBK) return 0;
     const int n_tiles = (N + kGemmTileN - 1) / kGemmTileN;
     int ns, kbp;
-    gemm_split(n_tiles, K / kGemmBK, &ns, &kbp);
+    gemm_split(n_tiles, K / kGemmBK, 16, &ns, &kbp);
     // sized for the largest split the heuristic (or the env override) may pick for any batch <= max_batch
     const size_t part = ns > 1 ? (size_t)ns * n_tiles * gemm_bpad(max_batch) * kGemmTileN * sizeof(float) : 0;
     return kGemmSemBytes + part;
@@ -457,8 +471,9 @@ int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const
         const char* tr = getenv("B200_GEMM_TRACE_PTR");   // developer timeline buffer (device pointer, 8*64 int64)
         p.trace = (tr && *tr) ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 0)) : nullptr;
     }
-    gemm_split(n_tiles, p.k_blocks, &p.nsplit, &p.kb_per_split);
-    if (p.nsplit > 1) {
+    p.cluster_reduce = env_int("B200_GEMM_CLUSTER", 1) ? 1 : 0;   // split-K merge through DSMEM (cluster <= 8) vs global semaphores
+    gemm_split(n_tiles, p.k_blocks, p.cluster_reduce ? 8 : 16, &p.nsplit, &p.kb_per_split);
+    if (p.nsplit > 1 && !p.cluster_reduce) {
         const size_t tile_bytes = (size_t)n_tiles * bpad * kGemmTileN * sizeof(float);
         if (!workspace || workspace_bytes < kGemmSemBytes + tile_bytes * 2) {
             p.nsplit = 1;  // no room for partials: fall back to one CTA per n-tile (still correct, just less parallel)

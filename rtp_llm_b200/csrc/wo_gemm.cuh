@@ -87,6 +87,7 @@ struct GemmParams {
     float* ws;               // [nsplit][n_tiles][bpad][128] fp32 split-K partials
     int* sem;                // [n_tiles], zero on entry / exit
     int use_pdl;
+    int cluster_reduce;      // 1: the nsplit CTAs of a tile form a cluster (1,nsplit,1) and merge through DSMEM
     long long* trace;        // developer timeline (tools/gemm_trace.py); null in production
     int dbg;                 // developer experiments (env B200_GEMM_DBG): 1 no math, 2 no TMEM store, 4 no MMA; 0 in production
 };
@@ -229,6 +230,15 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         atomicMin(reinterpret_cast<unsigned long long*>(&p.trace[8 * 64 + 14]), gt);   // earliest CTA start (ns)
+        {
+            const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+            if (cta < 1024) {
+                uint32_t smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                p.trace[8 * 64 + 16 + cta * 3 + 0] = smid;
+                p.trace[8 * 64 + 16 + cta * 3 + 1] = (long long)gt;
+            }
+        }
         if ((blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && blockIdx.y == 0) {
             const int o = blockIdx.x == 0 ? 0 : 4;
             p.trace[8 * 64 + o + 0] = clock64();
@@ -322,10 +332,25 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
         if (p.use_pdl && lane == 0) pdl_launch_dependents();
         int sw = 0, sx = 0, a = 0;
         uint32_t phw = 0, phx = 0, aph = 0;
+        bool x_ready = false, o_ready = false;
         for (int it = 0; it < nkb; ++it) {
-            mbar_wait(&xfull[sx], phx);
-            if (FMT == kFmtF16) mbar_wait(&wfull[sw], phw);
-            else mbar_wait(&afull[a], aph);
+            if (!x_ready) mbar_wait(&xfull[sx], phx);
+            if (!o_ready) {
+                if (FMT == kFmtF16) mbar_wait(&wfull[sw], phw);
+                else mbar_wait(&afull[a], aph);
+            }
+            // ring positions of the next block; probe them now, the answers come back while this block's MMAs issue
+            int sx_n = sx + 1, sw_n = sw + 1, a_n = a + 1;
+            uint32_t phx_n = phx, phw_n = phw, aph_n = aph;
+            if (sx_n == XS) { sx_n = 0; phx_n ^= 1; }
+            if (sw_n == WS) { sw_n = 0; phw_n ^= 1; }
+            if (a_n == A_STAGES) { a_n = 0; aph_n ^= 1; }
+            if (!(p.dbg & 16)) {
+                x_ready = o_ready = false;
+            } else if (it + 1 < nkb) {
+                x_ready = __all_sync(0xffffffffu, mbar_test(&xfull[sx_n], phx_n));
+                o_ready = __all_sync(0xffffffffu, (FMT == kFmtF16) ? mbar_test(&wfull[sw_n], phw_n) : mbar_test(&afull[a_n], aph_n));
+            }
             tc_fence_after();
             if (elect_one()) {
                 B200_TRACE(6, it);
@@ -351,18 +376,9 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
                 B200_TRACE(7, it);
             }
             __syncwarp();
-            if (++sx == XS) {
-                sx = 0;
-                phx ^= 1;
-            }
-            if (++sw == WS) {
-                sw = 0;
-                phw ^= 1;
-            }
-            if (++a == A_STAGES) {
-                a = 0;
-                aph ^= 1;
-            }
+            sx = sx_n; phx = phx_n;
+            sw = sw_n; phw = phw_n;
+            a = a_n; aph = aph_n;
         }
     } else {
         // ------------------------------------------------------------------ dequant warps (TMEM A producers)
@@ -375,11 +391,31 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
             int s = grp % WS, a = grp % A_STAGES, a_prev = 0;
             uint32_t ph = 0, aph = 0;
             bool first = true;
+            // barrier probes are issued one step ahead (test_wait is ~150 cycles even when the phase is complete): the
+            // answer for the weight stage of block it+GROUPS and for this block's TMEM buffer arrive under the math.
+            bool w_ready = false;
             for (int it = grp; it < nkb; it += GROUPS) {
-                mbar_wait(&wfull[s], ph);
+                if (!w_ready) mbar_wait(&wfull[s], ph);
                 if (threadIdx.x == 0) B200_TRACE(2, it);
                 const uint8_t* wb = wring + s * W_BYTES;
                 uint32_t regs[CPW][16];
+                bool a_free = false;
+                int s_n = s + GROUPS;
+                uint32_t ph_n = ph;
+                if (s_n >= WS) {
+                    s_n -= WS;
+                    ph_n ^= 1;
+                }
+#define PROBE_NEXT()                                                              \
+    do {                                                                          \
+        if (!(p.dbg & 16)) {   /* measured: probing ahead costs more than it hides; kept as experiment 16 */ \
+            a_free = false;                                                       \
+            w_ready = false;                                                      \
+            break;                                                                \
+        }                                                                         \
+        a_free = __all_sync(0xffffffffu, mbar_test(&aempty[a], aph ^ 1));         \
+        w_ready = (it + GROUPS < nkb) ? __all_sync(0xffffffffu, mbar_test(&wfull[s_n], ph_n)) : true; \
+    } while (0)
                 if (FMT == kFmtInt4) {
                     const uint16_t* sc = reinterpret_cast<const uint16_t*>(wb + 8192);
                     const typename Pair<T>::type s2 = Pair<T>::bcast(sc[row]);
@@ -391,6 +427,7 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
                     // the packed words are in registers: release the smem stage before doing the math
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&wempty[s]);
+                    PROBE_NEXT();
 #pragma unroll
                     for (int cc = 0; cc < CPW; ++cc) {
                         if (p.dbg & 1) {
@@ -412,6 +449,7 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
                             v[cc][h] = *reinterpret_cast<const uint4*>(wb + ((kc * CPW + cc) * 2 + h) * 2048 + row * 16);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&wempty[s]);
+                    PROBE_NEXT();
 #pragma unroll
                     for (int cc = 0; cc < CPW; ++cc)
 #pragma unroll
@@ -432,7 +470,7 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
                     if (threadIdx.x == 0) B200_TRACE(5, it);
                 }
                 first = false;
-                mbar_wait(&aempty[a], aph ^ 1);
+                if (!a_free) mbar_wait(&aempty[a], aph ^ 1);
                 if (threadIdx.x == 0) B200_TRACE(4, it);
                 tc_fence_after();
                 const uint32_t dst = tmem_a + lane_addr + a * 64 + kc * CPW * 16;
@@ -443,11 +481,8 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
                     for (int cc = 0; cc < CPW; ++cc) tmem_st_32x32b_x16(dst + cc * 16, regs[cc]);
                 }
                 a_prev = a;
-                s += GROUPS;
-                if (s >= WS) {
-                    s -= WS;
-                    ph ^= 1;
-                }
+                s = s_n;
+                ph = ph_n;
                 a += GROUPS;
                 if (a >= A_STAGES) {
                     a -= A_STAGES;
@@ -508,6 +543,16 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
                     if (n_ok && b < p.B) yp[(size_t)b * p.N + n] = from_f32<T>(fmaf(v[j], cscale, bias));
                 }
             }
+        } else if (p.cluster_reduce) {
+            // split-K merge through distributed shared memory: park the fp32 partial tile [bpad][128] in this CTA's smem
+            // (the activation ring is idle once the accumulator is final); the merge itself follows the cluster barrier below.
+            float* red = reinterpret_cast<float*>(xring);
+            for (int sl = kce; sl < SLICES; sl += KCS) {
+                float v[16];
+                load_acc(sl, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) red[(sl * 16 + j) * kGemmTileN + row] = v[j];
+            }
         } else {
             // write the fp32 partial tile [bpad][128] (coalesced along n), then the last CTA of this n-tile reduces
             float* wsp = p.ws + ((size_t)split * n_tiles + tile) * (size_t)(BPAD * kGemmTileN);
@@ -558,11 +603,46 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
         tc_fence_before();
     }
 
+    if (p.nsplit > 1 && p.cluster_reduce) {
+        // every thread of every CTA of the cluster (1, nsplit, 1) passes both barriers
+        cluster_sync_all();
+        if (warp < NDQ_WARPS) {
+            const int S = p.nsplit;
+            const int rank = (int)cluster_ctarank();          // == blockIdx.y
+            const int row = threadIdx.x & (kGemmTileN - 1);
+            const int lane_grp = threadIdx.x >> 7;             // NDQ_THREADS / 128 column lanes
+            const int n = tile * kGemmTileN + row;
+            const bool n_ok = n < p.N;
+            float cscale = 1.f, bias = 0.f;
+            if (n_ok) {
+                if (FMT == kFmtInt8) cscale = to_f32<T>(reinterpret_cast<const T*>(p.col_scale)[n]);
+                if (p.bias) bias = to_f32<T>(reinterpret_cast<const T*>(p.bias)[n]);
+            }
+            const float* red = reinterpret_cast<const float*>(xring);
+            T* yp = reinterpret_cast<T*>(p.y);
+            // CTA `rank` owns batch columns rank, rank+S, ...; fixed summation order sp = 0..S-1 (deterministic)
+            for (int b = rank + lane_grp * S; b < p.B; b += S * (NDQ_THREADS / kGemmTileN)) {
+                const uint32_t laddr = smem_u32(red + b * kGemmTileN + row);
+                float part[8];
+#pragma unroll
+                for (int sp = 0; sp < 8; ++sp) part[sp] = sp < S ? dsmem_ld_f32(dsmem_addr(laddr, sp)) : 0.f;
+                float acc = 0.f;
+#pragma unroll
+                for (int sp = 0; sp < 8; ++sp) acc += part[sp];
+                if (n_ok) yp[(size_t)b * p.N + n] = from_f32<T>(fmaf(acc, cscale, bias));
+            }
+        }
+        cluster_sync_all();   // peers may still be reading this CTA's partial
+    }
     __syncthreads();
     if (p.trace && threadIdx.x == 0) {
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         atomicMax(reinterpret_cast<unsigned long long*>(&p.trace[8 * 64 + 15]), gt);   // latest CTA end (ns)
+        {
+            const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+            if (cta < 1024) p.trace[8 * 64 + 16 + cta * 3 + 2] = (long long)gt;
+        }
         if ((blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && blockIdx.y == 0) {
             const int o = blockIdx.x == 0 ? 0 : 4;
             p.trace[8 * 64 + o + 1] = clock64();

@@ -78,6 +78,14 @@ class DecodeStep:
         g = torch.Generator(device="cpu").manual_seed(seed * 1000 + 17)
         H = cfg.hidden
 
+        def pack_ref(refw):
+            fmt = refw[0]
+            if fmt == "int4":
+                return ops.pack_w4(refw[1].to(device), refw[2].to(device), refw[3].to(device))
+            if fmt == "int8":
+                return ops.pack_w8(refw[1].to(device), refw[2].to(device))
+            return ops.pack_f16(refw[1].to(device))
+
         def make_weight(K: int, N: int, gen_seed: int, quant: Optional[str] = None):
             quant = quant or cfg.quant
             gg = torch.Generator(device=device).manual_seed(gen_seed)
@@ -101,13 +109,27 @@ class DecodeStep:
 
         self.layers: List[dict] = []
         qkv_n = (self.Hq + 2 * self.Hkv) * self.D
+        from . import tp as tpmod
+        shard_full = keep_reference and tp_size > 1      # parity runs: every rank builds the FULL weights, then slices
         for l in range(cfg.layers):
-            base = (seed * 100003 + l) * 16 + tp_rank * 7919
+            base = (seed * 100003 + l) * 16 + (0 if shard_full else tp_rank * 7919)
             L = {}
-            L["qkv"], r0 = make_weight(H, qkv_n, base + 1)
-            L["o"], r1 = make_weight(self.Hq * self.D, H, base + 2)
-            L["w13"], r2 = make_weight(H, 2 * self.inter, base + 3)
-            L["w2"], r3 = make_weight(self.inter, H, base + 4)
+            if shard_full:
+                _, f0 = make_weight(H, (cfg.head_num + 2 * cfg.kv_head_num) * self.D, base + 1)
+                _, f1 = make_weight(cfg.head_num * self.D, H, base + 2)
+                _, f2 = make_weight(H, 2 * cfg.inter, base + 3)
+                _, f3 = make_weight(cfg.inter, H, base + 4)
+                r0 = tpmod.shard_qkv(f0, cfg.head_num, cfg.kv_head_num, self.D, tp_rank, tp_size)
+                r1 = tpmod.shard_o(f1, cfg.head_num, self.D, tp_rank, tp_size)
+                r2 = tpmod.shard_w13(f2, cfg.inter, tp_rank, tp_size)
+                r3 = tpmod.shard_w2(f3, cfg.inter, tp_rank, tp_size)
+                L["qkv"], L["o"], L["w13"], L["w2"] = pack_ref(r0), pack_ref(r1), pack_ref(r2), pack_ref(r3)
+                L["full"] = dict(qkv=f0, o=f1, w13=f2, w2=f3)
+            else:
+                L["qkv"], r0 = make_weight(H, qkv_n, base + 1)
+                L["o"], r1 = make_weight(self.Hq * self.D, H, base + 2)
+                L["w13"], r2 = make_weight(H, 2 * self.inter, base + 3)
+                L["w2"], r3 = make_weight(self.inter, H, base + 4)
             L["ln1"] = (1.0 + 0.1 * torch.randn(H, generator=g)).to(dtype).to(device)
             L["ln2"] = (1.0 + 0.1 * torch.randn(H, generator=g)).to(dtype).to(device)
             L["kv"] = None
@@ -115,7 +137,12 @@ class DecodeStep:
                 L["ref"] = dict(qkv=r0, o=r1, w13=r2, w2=r3)
             self.layers.append(L)
         self.final_ln = (1.0 + 0.1 * torch.randn(H, generator=g)).to(dtype).to(device)
-        self.lm_head, self.lm_head_ref = make_weight(H, self.vocab, seed * 100003 + 999983 + tp_rank, quant="f16")
+        if shard_full:
+            _, self.lm_head_full = make_weight(H, cfg.vocab, seed * 100003 + 999983, quant="f16")
+            self.lm_head_ref = tpmod.shard_lm_head(self.lm_head_full, self.vocab, tp_rank)
+            self.lm_head = pack_ref(self.lm_head_ref)
+        else:
+            self.lm_head, self.lm_head_ref = make_weight(H, self.vocab, seed * 100003 + 999983 + tp_rank, quant="f16")
         gg = torch.Generator(device=device).manual_seed(seed + 5)
         self.embed = (torch.randn(cfg.vocab, H, generator=gg, device=device) * 0.5).to(dtype)
 

@@ -25,3 +25,66 @@ class NcclComm:
 
 def make_comm(device: torch.device, group=None):
     return NcclComm(device, group)
+
+
+# ------------------------------------------------------------------------------------------------ sharding
+# The reference's tensor-parallel split (rtp_llm/utils/model_weight.py:1489-1580): qkv column-parallel BY HEAD (sp_head,
+# :472-491), o row-parallel (sp_0), w1/w3 column-parallel (ffn_sp_neg1_w13, :997), w2 row-parallel (ffn_sp_0, :238),
+# scales / zeros split alongside, lm_head vocab rows (sp_0_pad8, :1491). Weights are the loader's UN-permuted tuples
+# (fmt, w, scales, zeros_x_scales): int4 w = uint8 [K, N/2]; int8 w = int8 [K, N], scales [N]; f16 w = [K, N].
+
+def _cols(wt, col_ranges):
+    """Select logical output columns [a, b) ranges of a reference-layout weight tuple."""
+    fmt, w, s, zs = wt
+    if fmt == "int4":
+        assert all(a % 2 == 0 and b % 2 == 0 for a, b in col_ranges)
+        wq = torch.cat([w[:, a // 2:b // 2] for a, b in col_ranges], dim=1).contiguous()
+        return (fmt, wq, torch.cat([s[:, a:b] for a, b in col_ranges], 1).contiguous(),
+                torch.cat([zs[:, a:b] for a, b in col_ranges], 1).contiguous())
+    wq = torch.cat([w[:, a:b] for a, b in col_ranges], dim=1).contiguous()
+    if fmt == "int8":
+        return (fmt, wq, torch.cat([s[a:b] for a, b in col_ranges]).contiguous(), None)
+    return (fmt, wq, None, None)
+
+
+def _rows(wt, a, b, group=128):
+    """Select input rows (the contraction dim) [a, b); group-wise scales follow in units of `group`."""
+    fmt, w, s, zs = wt
+    if fmt == "int4":
+        assert a % group == 0 and b % group == 0, "row-parallel INT4 shards must align to the quantisation group"
+        return (fmt, w[a:b].contiguous(), s[a // group:b // group].contiguous(), zs[a // group:b // group].contiguous())
+    return (fmt, w[a:b].contiguous(), s, None)
+
+
+def shard_qkv(wt, head_num, kv_head_num, head_dim, rank, tp):
+    hq, hkv = head_num // tp, max(kv_head_num // tp, 1)
+    kv_rank = rank if kv_head_num >= tp else rank * kv_head_num // tp      # replicated kv heads when Hkv < tp
+    q0 = rank * hq * head_dim
+    k_base, v_base = head_num * head_dim, (head_num + kv_head_num) * head_dim
+    k0 = k_base + kv_rank * hkv * head_dim
+    v0 = v_base + kv_rank * hkv * head_dim
+    return _cols(wt, [(q0, q0 + hq * head_dim), (k0, k0 + hkv * head_dim), (v0, v0 + hkv * head_dim)])
+
+
+def shard_o(wt, head_num, head_dim, rank, tp):
+    k = head_num // tp * head_dim
+    return _rows(wt, rank * k, (rank + 1) * k)
+
+
+def shard_w13(wt, inter, rank, tp):
+    i = inter // tp
+    return _cols(wt, [(rank * i, (rank + 1) * i), (inter + rank * i, inter + (rank + 1) * i)])
+
+
+def shard_w2(wt, inter, rank, tp):
+    i = inter // tp
+    return _rows(wt, rank * i, (rank + 1) * i)
+
+
+def shard_lm_head(wt, vocab_local, rank):
+    fmt, w, s, zs = wt
+    a, b = rank * vocab_local, (rank + 1) * vocab_local
+    part = w[:, a:min(b, w.shape[1])]
+    if part.shape[1] < vocab_local:                                          # sp_0_pad8: pad the last shard with zeros
+        part = torch.cat([part, torch.zeros(w.shape[0], vocab_local - part.shape[1], dtype=w.dtype, device=w.device)], 1)
+    return (fmt, part.contiguous(), None, None)

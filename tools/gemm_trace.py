@@ -20,7 +20,7 @@ x = torch.randn(B, K, device=dev).half()
 ws = ops.gemm_workspace(B, [(K, N)], dev)
 for _ in range(3):
     ops.wo_gemm(x, w, ws)
-trace = torch.zeros(8 * 64 + 16, dtype=torch.int64, device=dev)
+trace = torch.zeros(8 * 64 + 16 + 3 * 1024, dtype=torch.int64, device=dev)
 trace[8 * 64 + 14] = 2**62
 os.environ["B200_GEMM_TRACE_PTR"] = str(trace.data_ptr())
 st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -31,6 +31,7 @@ torch.cuda.synchronize()
 print("event-timed launch:", st.elapsed_time(en) * 1e3, "us")
 os.environ.pop("B200_GEMM_TRACE_PTR")
 ex = trace.cpu()[8 * 64:]
+res = trace.cpu()[8 * 64 + 16:].view(1024, 3)
 t = trace.cpu()[: 8 * 64].view(8, 64)
 t0 = int(t[0, 0])
 names = ["w_issue", "x_issue", "dq_wfull", "dq_math", "dq_aempty", "dq_afullarr", "mma_ready", "mma_issued"]
@@ -45,3 +46,20 @@ e = [int(v) - int(ex[0]) for v in ex[8:14]]
 print("epilogue (cycles since kernel entry): enter", e[0], "dfull", e[1], "partials stored", e[2], "fence+bar", e[3], "atomic+bar", e[4], "done", e[5], "| kernel end", int(ex[1]) - int(ex[0]))
 
 print("all CTAs: earliest start -> latest end:", int(ex[15]) - int(ex[14]), "ns")
+
+import collections
+t_min = int(ex[14])
+per_sm = collections.defaultdict(list)
+for c in range(1024):
+    if int(res[c, 1]) == 0:
+        continue
+    per_sm[int(res[c, 0])].append((int(res[c, 1]) - t_min, int(res[c, 2]) - t_min, c))
+overlap = 0
+for sm, lst in per_sm.items():
+    lst.sort()
+    for i in range(1, len(lst)):
+        if lst[i][0] < lst[i - 1][1]:
+            overlap += 1
+print("SMs used", len(per_sm), "CTAs", sum(len(v) for v in per_sm.values()), "pairs overlapping in time on one SM", overlap)
+for sm in sorted(per_sm)[:6]:
+    print("sm", sm, per_sm[sm])

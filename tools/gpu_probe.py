@@ -278,6 +278,9 @@ if __name__ == "__main__":
             gemm_case(f"gemm {nm} B16 K256 N256", fmt, 16, 256, 256)
             gemm_case(f"gemm {nm} B5 K512 N384 bias", fmt, 5, 512, 384, bias=True)
             gemm_case(f"gemm {nm} B32 K1024 N256 splitk4", fmt, 32, 1024, 256, env={"B200_GEMM_SPLITK": 4})
+            gemm_case(f"gemm {nm} B19 K1024 N256 splitk8 semaphore", fmt, 19, 1024, 256,
+                      env={"B200_GEMM_SPLITK": 8, "B200_GEMM_CLUSTER": 0})
+            gemm_case(f"gemm {nm} B19 K1024 N384 splitk3 bias cluster", fmt, 19, 1024, 384, env={"B200_GEMM_SPLITK": 3}, bias=True)
             gemm_case(f"gemm {nm} B33 K512 N200 (ragged N, bpad64)", fmt, 33, 512, 200)
             gemm_case(f"gemm {nm} B100 K512 N256 (bpad128)", fmt, 100, 512, 256)
             gemm_case(f"gemm {nm} bf16 B8 K256 N256", fmt, 8, 256, 256, dtype=torch.bfloat16)
