@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--ctx", type=int, default=2048)
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("B200_PDL", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--comm", default=os.environ.get("B200_COMM", "peer"), choices=["peer", "nccl"])
     return ap.parse_args()
 
 
@@ -193,7 +194,7 @@ def main():
     comm = None
     if tp > 1:
         dist.init_process_group("nccl", device_id=dev)
-        comm = make_comm(dev)
+        comm = make_comm(dev, kind=args.comm)
 
     model = DecodeStep(cfg, args.batch, args.ctx, dev, tp_rank=rank, tp_size=tp, comm=comm, pdl=bool(args.pdl))
     launches_per_step = model.launches_per_step()
@@ -273,7 +274,7 @@ def main():
             else f"f16 activations x {cfg.quant} weights, fp32 accumulate",
             "data": "synthetic (random-init weights of the named architecture, random page tables)",
             "config": {"workload": workload, "global_batch": args.batch, "seq_len": args.ctx,
-                       "parallelism": f"tp{tp}", "page_size": cfg.tokens_per_block, "cuda_graph": True,
+                       "parallelism": f"tp{tp}", "tp_allreduce": (args.comm if tp > 1 else None), "page_size": cfg.tokens_per_block, "cuda_graph": True,
                        "l2": "inputs larger than L2 (each step streams %.2f GB of weights + KV per GPU)" % (ab["total"] / 1e9),
                        "pdl": bool(args.pdl)},
             "e2e": {"value": args.batch / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": model.h2d_bytes(),
@@ -292,8 +293,14 @@ def main():
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
     if tp > 1:
+        # Teardown: process groups whose collectives were captured in CUDA graphs hang in destroy_process_group
+        # (observed: NCCL watchdog stuck in CudaEventDestroy). Drop the graph, sync, and leave without the destructor.
         dist.barrier()
-        dist.destroy_process_group()
+        model.graph = None
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

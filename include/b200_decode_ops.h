@@ -130,6 +130,22 @@ int b200_embedding(const int32_t* ids, const void* table, void* out, int is_bf16
 /* greedy sampling: out[r] = argmax(logits[r]) (lowest index on ties; CudaSampleOp.cc:330,453). dtype: 0 fp16, 1 bf16, 2 fp32 */
 int b200_argmax(const void* logits, int dtype, int rows, int vocab, int32_t* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ TP all-reduce over NVLink peer memory */
+
+/* One-shot SUM all-reduce of a small [rows][hidden] fp16/bf16 tensor, the exchange after each row-parallel GEMM
+ * (replaces all_reduce(t, Group.TP), rtp_llm/models_py/distributed/collective_torch.py:694-722; the reference's fast path
+ * is torch symmetric memory, distributed/symm_mem.py:126-185). One process per GPU. Set-up, once per process:
+ *   b200_peer_alloc(b200_peer_ar_region_bytes(max_msg), &mine, handle)  -> exchange the 64-byte handles between ranks
+ *   (any host channel) -> b200_peer_open(handle_of_rank_r, &regions[r]) for r != rank; regions[rank] = mine.
+ * Per call: `call_parity` must alternate 0,1,0,1,... between consecutive calls on the stream (two data slots), and every
+ * rank must issue the same sequence of calls. Deterministic: all ranks sum in rank order and get identical bits.
+ * CUDA-graph capturable (call counters live on the device). bytes % 16 == 0, bytes <= max_message_bytes, world <= 8. */
+size_t b200_peer_ar_region_bytes(size_t max_message_bytes);
+int b200_peer_alloc(size_t bytes, void** ptr, void* ipc_handle_out);
+int b200_peer_open(const void* ipc_handle, void** ptr);
+int b200_peer_allreduce(const void* in, void* out, size_t bytes, int is_bf16, void* const* regions, size_t max_message_bytes,
+                        int call_parity, int rank, int world, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ GPU-side checkers */
 /* Deliberately naive CUDA-core kernels over the UN-permuted reference tensors; used by tests only. */
 int b200_ref_paged_decode_attn(const void* q, int is_bf16, void* out, int head_num, int kv_head_num, int head_dim,

@@ -31,6 +31,10 @@ SIGNATURES = {
     "b200_rope_append": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_float, c_void_p]),
     "b200_embedding": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200_argmax": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b200_peer_ar_region_bytes": (c_size_t, [c_size_t]),
+    "b200_peer_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
+    "b200_peer_open": (c_int, [c_void_p, c_void_p]),
+    "b200_peer_allreduce": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
     "b200_ref_paged_decode_attn": (c_int, [c_void_p, c_int, c_void_p] + [c_int] * 6 + [c_void_p] * 3 + [c_float, c_void_p]),
     "b200_ref_dequant_gemm": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_int] + [c_void_p] * 3 + [c_int, c_void_p,
                                       c_void_p, c_void_p]),

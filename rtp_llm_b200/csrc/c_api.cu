@@ -15,6 +15,7 @@
 #include "../../include/b200_decode_ops.h"
 #include "aux_kernels.cuh"
 #include "paged_decode_attn.cuh"
+#include "peer_allreduce.cuh"
 #include "wo_gemm.cuh"
 
 using namespace b200;
@@ -589,6 +590,67 @@ int b200_argmax(const void* logits, int dtype, int rows, int vocab, int32_t* out
     else
         argmax_kernel<float><<<rows, 1024, 0, (cudaStream_t)stream>>>((const float*)logits, vocab, out);
     return launched("argmax_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------ peer all-reduce
+size_t b200_peer_ar_region_bytes(size_t max_message_bytes) {
+    // [2 data slots][flags W x CTAs][epochs]
+    return 2 * round_up(max_message_bytes, 256) + kArMaxWorld * kArMaxCtas * sizeof(uint32_t) + kArMaxCtas * sizeof(uint32_t) + 256;
+}
+
+int b200_peer_alloc(size_t bytes, void** ptr, void* ipc_handle_out /*64 bytes*/) {
+    ARG_CHECK(ptr && ipc_handle_out && bytes > 0, "peer_alloc: bad argument");
+    void* d = nullptr;
+    CUDA_CHECK(cudaMalloc(&d, bytes));
+    CUDA_CHECK(cudaMemset(d, 0, bytes));
+    CUDA_CHECK(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    CUDA_CHECK(cudaIpcGetMemHandle(&h, d));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(ipc_handle_out, &h, sizeof(h));
+    *ptr = d;
+    return B200_OK;
+}
+
+int b200_peer_open(const void* ipc_handle /*64 bytes*/, void** ptr) {
+    ARG_CHECK(ipc_handle && ptr, "peer_open: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof(h));
+    void* d = nullptr;
+    CUDA_CHECK(cudaIpcOpenMemHandle(&d, h, cudaIpcMemLazyEnablePeerAccess));
+    *ptr = d;
+    return B200_OK;
+}
+
+int b200_peer_allreduce(const void* in, void* out, size_t bytes, int is_bf16, void* const* regions, size_t max_message_bytes,
+                        int call_parity, int rank, int world, void* stream) {
+    ARG_CHECK(in && out && regions, "peer_allreduce: null pointer");
+    ARG_CHECK(world >= 2 && world <= kArMaxWorld && rank >= 0 && rank < world, "peer_allreduce: bad rank/world %d/%d", rank, world);
+    ARG_CHECK(bytes > 0 && bytes % 16 == 0 && bytes <= max_message_bytes, "peer_allreduce: message of %zu bytes unsupported", bytes);
+    ARG_CHECK((((uintptr_t)in | (uintptr_t)out) & 15) == 0, "peer_allreduce: in/out must be 16-byte aligned");
+    const size_t slot_b = round_up(max_message_bytes, 256);
+    PeerArParams p{};
+    p.in = in;
+    p.out = out;
+    for (int r = 0; r < world; ++r) {
+        uint8_t* base = reinterpret_cast<uint8_t*>(regions[r]);
+        ARG_CHECK(base, "peer_allreduce: region %d is null", r);
+        p.slot[r] = base + (call_parity & 1) * slot_b;
+        p.flags[r] = reinterpret_cast<uint32_t*>(base + 2 * slot_b);
+    }
+    p.epoch = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(regions[rank]) + 2 * slot_b +
+                                          kArMaxWorld * kArMaxCtas * sizeof(uint32_t));
+    p.n16 = (int)(bytes / 16);
+    p.rank = rank;
+    p.world = world;
+    int ctas = (p.n16 + kArThreads - 1) / kArThreads;
+    if (ctas > kArMaxCtas) ctas = kArMaxCtas;
+    const bool pdl = g_pdl.load() != 0;
+    if (is_bf16)
+        CUDA_CHECK(launch_ex(peer_allreduce_kernel<__nv_bfloat16>, dim3(ctas), dim3(kArThreads), 0, (cudaStream_t)stream, pdl, p));
+    else
+        CUDA_CHECK(launch_ex(peer_allreduce_kernel<__half>, dim3(ctas), dim3(kArThreads), 0, (cudaStream_t)stream, pdl, p));
+    return launched("peer_allreduce_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------ GPU-side checkers

@@ -235,7 +235,7 @@ class DecodeStep:
         ops.wo_gemm(self.x, self.lm_head, self.gemm_ws, out=self.logits, pdl=self.pdl)
         if self.tp_size > 1:
             self.comm.all_gather(self.logits_all, self.logits)
-            full = self.logits_all.permute(1, 0, 2).reshape(self.B, -1)
+            full = self.logits_all.permute(1, 0, 2).reshape(self.B, -1)[:, : self.cfg.vocab]   # drop the sp_0_pad8 columns
             self.next_ids.copy_(torch.argmax(full.float(), dim=-1).to(torch.int32))  # next: own kernel over the gathered view
         else:
             ops.argmax(self.logits, out=self.next_ids)

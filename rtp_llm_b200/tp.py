@@ -23,8 +23,52 @@ class NcclComm:
         dist.all_gather_into_tensor(out, t, group=self.group)
 
 
-def make_comm(device: torch.device, group=None):
-    return NcclComm(device, group)
+class PeerComm(NcclComm):
+    """TP all-reduce through our own one-shot kernel over NVLink peer memory (csrc/peer_allreduce.cuh): each rank
+    cudaMalloc's a peer-visible region, the 64-byte IPC handles travel over the existing process group, and the kernel
+    reads all peers' slots directly. The (once per step, 2 MB) logits all-gather stays on NCCL."""
+
+    MAX_MESSAGE = 1 << 20   # decode all-reduces are [B, hidden] fp16: 256 KiB at the BASELINE configs
+
+    def __init__(self, device: torch.device, group=None):
+        super().__init__(device, group)
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        self._lib, self._ct = lib, ctypes
+        nbytes = lib.b200_peer_ar_region_bytes(self.MAX_MESSAGE)
+        mine = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        _lib.check(lib.b200_peer_alloc(nbytes, ctypes.byref(mine), handle), "b200_peer_alloc")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        ptrs = []
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs.append(mine.value)
+            else:
+                p = ctypes.c_void_p()
+                hb = ctypes.create_string_buffer(handles[r], 64)
+                _lib.check(lib.b200_peer_open(hb, ctypes.byref(p)), "b200_peer_open")
+                ptrs.append(p.value)
+        self._regions = (ctypes.c_void_p * self.world)(*ptrs)
+        self._calls = 0
+        dist.barrier(group=group)     # every rank has zeroed + mapped every region before the first kernel
+
+    def all_reduce(self, t: torch.Tensor) -> None:
+        from . import _lib
+        nbytes = t.numel() * t.element_size()
+        if nbytes > self.MAX_MESSAGE or nbytes % 16 or not t.is_contiguous():
+            return super().all_reduce(t)
+        _lib.check(self._lib.b200_peer_allreduce(t.data_ptr(), t.data_ptr(), nbytes, 1 if t.dtype == torch.bfloat16 else 0,
+                                                 self._regions, self.MAX_MESSAGE, self._calls & 1, self.rank, self.world,
+                                                 torch.cuda.current_stream().cuda_stream), "b200_peer_allreduce")
+        self._calls += 1
+
+
+def make_comm(device: torch.device, group=None, kind: str = "peer"):
+    """kind: "peer" (our NVLink kernel) or "nccl" (stock collectives, the baseline arm)."""
+    return PeerComm(device, group) if kind == "peer" else NcclComm(device, group)
 
 
 # ------------------------------------------------------------------------------------------------ sharding
