@@ -30,6 +30,8 @@ extern "C" {
 
 /* flags of b200_wo_gemm */
 #define B200_GEMM_PDL 1  /* launch with programmatic dependent launch (weights prefetched before the upstream grid ends) */
+#define B200_GEMM_SILU_MUL 2 /* fused SiLU(gate)*up epilogue: the weight's columns were interleaved per 128-feature tile as
+                                [64 gate | 64 matching up] BEFORE packing (rtp_llm_b200.ops.interleave_gate_up); y is [B][N/2] */
 
 /* Last error message of the calling thread ("" if none). */
 const char* b200_last_error(void);

@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(HERE, "libb200_decode.so")
 
 B200_FMT_F16, B200_FMT_INT8, B200_FMT_INT4 = 0, 1, 2
 B200_GEMM_PDL = 1
+B200_GEMM_SILU_MUL = 2
 
 # name -> (restype, argtypes): mirrors include/b200_decode_ops.h one to one (tests check every symbol resolves)
 SIGNATURES = {

@@ -467,6 +467,8 @@ int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const
     p.K = K;
     p.k_blocks = K / kGemmBK;
     p.use_pdl = ((flags & B200_GEMM_PDL) || g_pdl.load()) ? 1 : 0;
+    p.silu_mul = (flags & B200_GEMM_SILU_MUL) ? 1 : 0;
+    ARG_CHECK(!p.silu_mul || N % 128 == 0, "wo_gemm: SILU_MUL needs N %% 128 == 0 (gate/up interleaved in 64-feature halves)");
     p.dbg = env_int("B200_GEMM_DBG", 0);
     {
         const char* tr = getenv("B200_GEMM_TRACE_PTR");   // developer timeline buffer (device pointer, 8*64 int64)
@@ -474,6 +476,10 @@ int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const
     }
     p.cluster_reduce = env_int("B200_GEMM_CLUSTER", 1) ? 1 : 0;   // split-K merge through DSMEM (cluster <= 8) vs global semaphores
     gemm_split(n_tiles, p.k_blocks, p.cluster_reduce ? 8 : 16, &p.nsplit, &p.kb_per_split);
+    if (p.silu_mul && !p.cluster_reduce) {
+        p.nsplit = 1;   // the fused activation is implemented for the direct and the cluster-merge epilogues
+        p.kb_per_split = p.k_blocks;
+    }
     if (p.nsplit > 1 && !p.cluster_reduce) {
         const size_t tile_bytes = (size_t)n_tiles * bpad * kGemmTileN * sizeof(float);
         if (!workspace || workspace_bytes < kGemmSemBytes + tile_bytes * 2) {
@@ -643,7 +649,10 @@ int b200_peer_allreduce(const void* in, void* out, size_t bytes, int is_bf16, vo
     p.n16 = (int)(bytes / 16);
     p.rank = rank;
     p.world = world;
-    int ctas = (p.n16 + kArThreads - 1) / kArThreads;
+    int ctas = (p.n16 + 4 * kArThreads - 1) / (4 * kArThreads);   // >= 4 chunks (64 B) per thread: fewer flags to exchange
+    if (ctas > kArMaxCtas) ctas = kArMaxCtas;
+    if (ctas < 1) ctas = 1;
+    ctas = env_int("B200_AR_CTAS", ctas);
     if (ctas > kArMaxCtas) ctas = kArMaxCtas;
     const bool pdl = g_pdl.load() != 0;
     if (is_bf16)

@@ -70,9 +70,9 @@ __global__ void __launch_bounds__(kArThreads) peer_allreduce_kernel(const PeerAr
     const uint4* src = reinterpret_cast<const uint4*>(p.in);
     uint4* mine = reinterpret_cast<uint4*>(p.slot[p.rank]);
     for (int i = c0 + threadIdx.x; i < c1; i += kArThreads) mine[i] = src[i];
-    __threadfence_system();
     __syncthreads();
-    // 2) one flag per (peer, CTA): "rank `rank`, CTA `cta` has published call `epoch`"
+    // 2) one flag per (peer, CTA): "rank `rank`, CTA `cta` has published call `epoch`". The release store of a thread that
+    //    passed the CTA barrier is cumulative over the other threads' stores -- no per-thread system fence needed.
     if (threadIdx.x < p.world) st_release_sys(p.flags[threadIdx.x] + p.rank * kArMaxCtas + cta, epoch);
     // 3) wait until every rank's matching CTA has published
     if (threadIdx.x < p.world) {

@@ -87,6 +87,7 @@ struct GemmParams {
     float* ws;               // [nsplit][n_tiles][bpad][128] fp32 split-K partials
     int* sem;                // [n_tiles], zero on entry / exit
     int use_pdl;
+    int silu_mul;            // 1: tile rows 0-63 are gate features, rows 64-127 the matching up features; y[b][tile*64+r] = silu(g)*u
     int cluster_reduce;      // 1: the nsplit CTAs of a tile form a cluster (1,nsplit,1) and merge through DSMEM
     long long* trace;        // developer timeline (tools/gemm_trace.py); null in production
     int dbg;                 // developer experiments (env B200_GEMM_DBG): 1 no math, 2 no TMEM store, 4 no MMA; 0 in production
@@ -519,6 +520,7 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
             if (FMT == kFmtInt8) cscale = to_f32<T>(reinterpret_cast<const T*>(p.col_scale)[n]);
             if (p.bias) bias = to_f32<T>(reinterpret_cast<const T*>(p.bias)[n]);
         }
+        float* fin = reinterpret_cast<float*>(wring);       // [bpad][128] fp32 staging for the fused SiLU*mul (weight ring is idle)
         // 16 batch columns of this thread's feature row, summed over the NACC accumulator tiles
         auto load_acc = [&](int sl, float (&v)[16]) {
             uint32_t r[NACC][16];
@@ -540,7 +542,8 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int b = sl * 16 + j;
-                    if (n_ok && b < p.B) yp[(size_t)b * p.N + n] = from_f32<T>(fmaf(v[j], cscale, bias));
+                    if (p.silu_mul) fin[b * kGemmTileN + row] = fmaf(v[j], cscale, bias);
+                    else if (n_ok && b < p.B) yp[(size_t)b * p.N + n] = from_f32<T>(fmaf(v[j], cscale, bias));
                 }
             }
         } else if (p.cluster_reduce) {
@@ -629,10 +632,30 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
                 float acc = 0.f;
 #pragma unroll
                 for (int sp = 0; sp < 8; ++sp) acc += part[sp];
-                if (n_ok) yp[(size_t)b * p.N + n] = from_f32<T>(fmaf(acc, cscale, bias));
+                if (p.silu_mul) reinterpret_cast<float*>(wring)[b * kGemmTileN + row] = fmaf(acc, cscale, bias);
+                else if (n_ok) yp[(size_t)b * p.N + n] = from_f32<T>(fmaf(acc, cscale, bias));
             }
         }
         cluster_sync_all();   // peers may still be reading this CTA's partial
+    }
+    if (p.silu_mul) {
+        // fused SiLU(gate) * up (replaces rtp_llm_ops.silu_and_mul after the w13 GEMM, modules/hybrid/dense_mlp.py:95-106)
+        __syncthreads();
+        if (warp < NDQ_WARPS) {
+            const float* fin = reinterpret_cast<const float*>(wring);
+            T* yp = reinterpret_cast<T*>(p.y);
+            const int n_out = p.N / 2;
+            const int S = (p.nsplit > 1 && p.cluster_reduce) ? p.nsplit : 1;
+            const int rank = S > 1 ? (int)cluster_ctarank() : 0;
+            for (int idx = threadIdx.x; idx < BPAD * 64; idx += NDQ_THREADS) {
+                const int b = idx >> 6, r = idx & 63;
+                if (b >= p.B || (b % S) != rank) continue;      // with a cluster merge each CTA owns the columns b % S == rank
+                const int j = tile * 64 + r;
+                if (j >= n_out) continue;
+                const float g = fin[b * kGemmTileN + r], u = fin[b * kGemmTileN + 64 + r];
+                yp[(size_t)b * n_out + j] = from_f32<T>(g / (1.f + __expf(-g)) * u);
+            }
+        }
     }
     __syncthreads();
     if (p.trace && threadIdx.x == 0) {

@@ -61,7 +61,7 @@ class DecodeStep:
 
     def __init__(self, cfg: ModelConfig, batch: int, ctx: int, device: torch.device, tp_rank: int = 0, tp_size: int = 1,
                  dtype=torch.float16, seed: int = 0, keep_reference: bool = False, ragged: bool = False,
-                 pdl: bool = False, comm=None):
+                 pdl: bool = False, comm=None, fuse_silu: bool = True):
         assert cfg.head_num % tp_size == 0 and cfg.inter % tp_size == 0
         self.cfg, self.B, self.ctx, self.dev, self.dtype = cfg, batch, ctx, device, dtype
         self.tp_rank, self.tp_size, self.comm, self.pdl = tp_rank, tp_size, comm, pdl
@@ -75,18 +75,32 @@ class DecodeStep:
         T = cfg.tokens_per_block
         self.M = (ctx + T - 1) // T
         self.ref: Dict[str, list] = {} if keep_reference else None
+        self.fuse_silu = fuse_silu and self.inter % 64 == 0
         g = torch.Generator(device="cpu").manual_seed(seed * 1000 + 17)
         H = cfg.hidden
 
-        def pack_ref(refw):
-            fmt = refw[0]
+        def pack_ref(refw, gate_up_inter: int = 0):
+            """Reference-layout tuple -> kernel layout. gate_up_inter > 0: a [K, 2I] gate|up weight whose columns are
+            first interleaved per 64 outputs so the GEMM epilogue can apply SiLU(gate)*up (ops.interleave_gate_up)."""
+            fmt, w, s, zs = refw
+            gi = gate_up_inter
             if fmt == "int4":
-                return ops.pack_w4(refw[1].to(device), refw[2].to(device), refw[3].to(device))
+                w, s, zs = w.to(device), s.to(device), zs.to(device)
+                if gi:
+                    w, s, zs = (ops.interleave_gate_up(w, gi, packed_int4=True), ops.interleave_gate_up(s, gi),
+                                ops.interleave_gate_up(zs, gi))
+                return ops.pack_w4(w, s, zs)
             if fmt == "int8":
-                return ops.pack_w8(refw[1].to(device), refw[2].to(device))
-            return ops.pack_f16(refw[1].to(device))
+                w, s = w.to(device), s.to(device)
+                if gi:
+                    w, s = ops.interleave_gate_up(w, gi), ops.interleave_gate_up(s, gi)
+                return ops.pack_w8(w, s)
+            w = w.to(device)
+            if gi:
+                w = ops.interleave_gate_up(w, gi)
+            return ops.pack_f16(w)
 
-        def make_weight(K: int, N: int, gen_seed: int, quant: Optional[str] = None):
+        def make_weight(K: int, N: int, gen_seed: int, quant: Optional[str] = None, gate_up_inter: int = 0):
             quant = quant or cfg.quant
             gg = torch.Generator(device=device).manual_seed(gen_seed)
             if quant == "int4":
@@ -94,17 +108,15 @@ class DecodeStep:
                 s = (torch.randn(K // 128, N, generator=gg, device=device).abs() * 0.01 + 1e-3).to(dtype)
                 z = torch.randint(0, 16, (K // 128, N), generator=gg, device=device)
                 zs = ((8 - z).to(dtype) * s).to(dtype)
-                w = ops.pack_w4(qp, s, zs)
                 refw = ("int4", qp, s, zs)
             elif quant == "int8":
                 q8 = torch.randint(-128, 128, (K, N), generator=gg, device=device, dtype=torch.int8)
                 s = (torch.randn(N, generator=gg, device=device).abs() * 2e-4 + 1e-5).to(dtype)
-                w = ops.pack_w8(q8, s)
                 refw = ("int8", q8, s, None)
             else:
                 wkn = (torch.randn(K, N, generator=gg, device=device) * 0.02).to(dtype)
-                w = ops.pack_f16(wkn)
                 refw = ("f16", wkn, None, None)
+            w = pack_ref(refw, gate_up_inter)
             return w, (tuple(t.cpu() if torch.is_tensor(t) else t for t in refw) if keep_reference else None)
 
         self.layers: List[dict] = []
@@ -123,12 +135,13 @@ class DecodeStep:
                 r1 = tpmod.shard_o(f1, cfg.head_num, self.D, tp_rank, tp_size)
                 r2 = tpmod.shard_w13(f2, cfg.inter, tp_rank, tp_size)
                 r3 = tpmod.shard_w2(f3, cfg.inter, tp_rank, tp_size)
-                L["qkv"], L["o"], L["w13"], L["w2"] = pack_ref(r0), pack_ref(r1), pack_ref(r2), pack_ref(r3)
+                L["qkv"], L["o"], L["w2"] = pack_ref(r0), pack_ref(r1), pack_ref(r3)
+                L["w13"] = pack_ref(r2, self.inter if self.fuse_silu else 0)
                 L["full"] = dict(qkv=f0, o=f1, w13=f2, w2=f3)
             else:
                 L["qkv"], r0 = make_weight(H, qkv_n, base + 1)
                 L["o"], r1 = make_weight(self.Hq * self.D, H, base + 2)
-                L["w13"], r2 = make_weight(H, 2 * self.inter, base + 3)
+                L["w13"], r2 = make_weight(H, 2 * self.inter, base + 3, gate_up_inter=self.inter if self.fuse_silu else 0)
                 L["w2"], r3 = make_weight(self.inter, H, base + 4)
             L["ln1"] = (1.0 + 0.1 * torch.randn(H, generator=g)).to(dtype).to(device)
             L["ln2"] = (1.0 + 0.1 * torch.randn(H, generator=g)).to(dtype).to(device)
@@ -227,8 +240,11 @@ class DecodeStep:
             ops.wo_gemm(self.attn, L["o"], self.gemm_ws, out=self.proj, pdl=self.pdl)
             self._all_reduce(self.proj)
             ops.add_rmsnorm(self.proj, self.resid, L["ln2"], cfg.eps, out=self.x)
-            ops.wo_gemm(self.x, L["w13"], self.gemm_ws, out=self.gu, pdl=self.pdl)
-            ops.silu_and_mul(self.gu, out=self.act)
+            if self.fuse_silu:     # SiLU(gate)*up in the GEMM epilogue (gate/up columns interleaved at load time)
+                ops.wo_gemm(self.x, L["w13"], self.gemm_ws, out=self.act, pdl=self.pdl, silu_mul=True)
+            else:
+                ops.wo_gemm(self.x, L["w13"], self.gemm_ws, out=self.gu, pdl=self.pdl)
+                ops.silu_and_mul(self.gu, out=self.act)
             ops.wo_gemm(self.act, L["w2"], self.gemm_ws, out=self.proj, pdl=self.pdl)
             self._all_reduce(self.proj)
         ops.add_rmsnorm(self.proj, self.resid, self.final_ln, cfg.eps, out=self.x)

@@ -141,16 +141,34 @@ def gemm_workspace(max_batch: int, shapes, device) -> torch.Tensor:
     return torch.zeros(max(n, 256), dtype=torch.uint8, device=device)
 
 
+def gate_up_order(inter: int, device=None) -> torch.Tensor:
+    """Column order that puts, for every 64 outputs j, [gate j .. j+63 | up j .. j+63] into one 128-feature tile: the
+    layout the fused SiLU*mul epilogue (B200_GEMM_SILU_MUL) expects of a [K, 2*inter] gate|up weight."""
+    assert inter % 64 == 0
+    j = torch.arange(inter, device=device).reshape(-1, 64)
+    return torch.cat([j, j + inter], dim=1).reshape(-1)
+
+
+def interleave_gate_up(w: torch.Tensor, inter: int, packed_int4: bool = False) -> torch.Tensor:
+    """Apply gate_up_order to the column axis of a reference-layout tensor ([K, 2I], or uint8 [K, I] packed int4,
+    or scales [G, 2I] / [2I])."""
+    order = gate_up_order(inter, w.device)
+    if packed_int4:
+        order = order.reshape(-1, 2)[:, 0] // 2          # byte index of every column pair (64 is even)
+    return w.index_select(-1, order).contiguous()
+
+
 def wo_gemm(x: torch.Tensor, w: PackedWeight, workspace: torch.Tensor, bias: Optional[torch.Tensor] = None,
-            out: Optional[torch.Tensor] = None, pdl: bool = False) -> torch.Tensor:
+            out: Optional[torch.Tensor] = None, pdl: bool = False, silu_mul: bool = False) -> torch.Tensor:
     _cuda_contig(x, w.data, workspace, bias, out)
     B, K = x.shape
     if K != w.K:
         raise B200Error(f"wo_gemm: x has K={K}, weight has K={w.K}")
     if out is None:
-        out = torch.empty((B, w.N), dtype=x.dtype, device=x.device)
+        out = torch.empty((B, w.N // 2 if silu_mul else w.N), dtype=x.dtype, device=x.device)
     check(_lib.load().b200_wo_gemm(w.fmt, _is_bf16(x), _p(x), B, K, w.N, _p(w.data), _p(w.col_scale), _p(bias), _p(out),
-                                   _p(workspace), workspace.numel(), _lib.B200_GEMM_PDL if pdl else 0, _stream()),
+                                   _p(workspace), workspace.numel(),
+                                   (_lib.B200_GEMM_PDL if pdl else 0) | (_lib.B200_GEMM_SILU_MUL if silu_mul else 0), _stream()),
           "b200_wo_gemm")
     return out
 

@@ -105,6 +105,16 @@ def test_gemm_full_size_vs_naive_gpu_kernel(cfg):
     _run(probe.gemm_case, name, fmt, B, K, N, big=True)
 
 
+@pytest.mark.parametrize("fmt", [B200_FMT_F16, B200_FMT_INT8, B200_FMT_INT4], ids=["f16", "int8", "int4"])
+def test_gemm_fused_silu_mul_vs_oracle(fmt):
+    _run(probe.gemm_silu_case, "silu direct", fmt, 7, 256, 192)
+    _run(probe.gemm_silu_case, "silu cluster split", fmt, 32, 1024, 128, env={"B200_GEMM_SPLITK": 4})
+
+
+def test_gemm_semaphore_split_path_still_correct():
+    _run(probe.gemm_case, "semaphore split", B200_FMT_INT4, 19, 1024, 256, env={"B200_GEMM_SPLITK": 8, "B200_GEMM_CLUSTER": 0})
+
+
 def test_gemm_is_linear_in_x():
     """Size-independent property at a BASELINE shape: Y(a*x1 + x2) == a*Y(x1) + Y(x2) within fp16 rounding."""
     dev = torch.device("cuda")

@@ -200,6 +200,49 @@ def gemm_case(name, fmt, B, K, N, dtype=torch.float16, simple=False, onehot=Fals
     guard(name, fn)
 
 
+def gemm_silu_case(name, fmt, B, K, inter, dtype=torch.float16, env=None):
+    """w13 GEMM with the fused SiLU*mul epilogue vs oracle (GEMM on the un-permuted weight, then silu_and_mul)."""
+    def fn():
+        old = {}
+        for k, v in (env or {}).items():
+            old[k] = os.environ.get(k)
+            os.environ[k] = str(v)
+        try:
+            rng = np.random.default_rng(9)
+            N = 2 * inter
+            x = torch.from_numpy(rng.standard_normal((B, K)).astype(np.float32)).to(dtype).to(dev)
+            bits = lambda t: t.cpu().contiguous().view(torch.int16).numpy().view(np.uint16)
+            if fmt == B200_FMT_INT4:
+                qp, s, zs = make_w4(K, N)
+                qd, sd, zd = torch.from_numpy(qp).to(dev), torch.from_numpy(s).to(dtype).to(dev), torch.from_numpy(zs).to(dtype).to(dev)
+                w = ops.pack_w4(ops.interleave_gate_up(qd, inter, packed_int4=True), ops.interleave_gate_up(sd, inter),
+                                ops.interleave_gate_up(zd, inter))
+                gu = orc.dequant_gemm(bits(x), "int4", qp, scales=bits(sd), zeros_x_scales=bits(zd), group=128)
+            elif fmt == B200_FMT_INT8:
+                q8 = rng.integers(-128, 128, (K, N)).astype(np.int8)
+                s = (np.abs(rng.standard_normal(N)) * 2e-4 + 3e-4).astype(np.float32)
+                qd, sd = torch.from_numpy(q8).to(dev), torch.from_numpy(s).to(dtype).to(dev)
+                w = ops.pack_w8(ops.interleave_gate_up(qd, inter), ops.interleave_gate_up(sd, inter))
+                gu = orc.dequant_gemm(bits(x), "int8", q8, scales=bits(sd))
+            else:
+                wd = torch.from_numpy((rng.standard_normal((K, N)) * 0.05).astype(np.float32)).to(dtype).to(dev)
+                w = ops.pack_f16(ops.interleave_gate_up(wd, inter))
+                gu = orc.dequant_gemm(bits(x), "f16", bits(wd))
+            exp = orc.from_bits(orc.silu_and_mul(gu), False)
+            ws = ops.gemm_workspace(B, [(K, N)], dev)
+            y = ops.wo_gemm(x, w, ws, silu_mul=True)
+            torch.cuda.synchronize()
+            ok, info = diff_info(y, exp, 2e-2, 2e-2)
+            report(name + " [fused silu*mul vs oracle]", ok and tuple(y.shape) == (B, inter), info)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    guard(name, fn)
+
+
 def glue_cases():
     def fn():
         rng = np.random.default_rng(3)
@@ -284,6 +327,8 @@ if __name__ == "__main__":
             gemm_case(f"gemm {nm} B33 K512 N200 (ragged N, bpad64)", fmt, 33, 512, 200)
             gemm_case(f"gemm {nm} B100 K512 N256 (bpad128)", fmt, 100, 512, 256)
             gemm_case(f"gemm {nm} bf16 B8 K256 N256", fmt, 8, 256, 256, dtype=torch.bfloat16)
+            gemm_silu_case(f"gemm {nm} silu B7 K256 I192", fmt, 7, 256, 192)
+            gemm_silu_case(f"gemm {nm} silu B32 K1024 I128 cluster split 4", fmt, 32, 1024, 128, env={"B200_GEMM_SPLITK": 4})
     if "gemm" in which or "gemm:big" in which:
         gemm_case("gemm int4 Llama qkv B32", B200_FMT_INT4, 32, 4096, 6144, big=True)
         gemm_case("gemm int4 Llama w2 B32", B200_FMT_INT4, 32, 14336, 4096, big=True)
