@@ -10,7 +10,9 @@ LIB = os.path.join(HERE, "libb200_decode.so")
 SOURCES = ["c_api.cu"]
 HEADERS = ["ptx.cuh", "paged_decode_attn.cuh", "wo_gemm.cuh", "aux_kernels.cuh", "../../include/b200_decode_ops.h"]
 NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-shared",
-              "-Xcompiler", "-fPIC", "--use_fast_math" if False else "-DB200_BUILD"]
+              "-Xcompiler", "-fPIC", "-DB200_BUILD"]
+if os.environ.get("B200_DEV"):           # developer build: clock64 timeline + ablation switches in the GEMM (tools/gemm_trace.py)
+    NVCC_FLAGS.append("-DB200_GEMM_DEV")
 
 
 def _stale() -> bool:

@@ -227,10 +227,7 @@ int gemm_variant() {
 }
 template <int FMT, typename T, int BPAD>
 int launch_gemm(const CUtensorMap& xmap, const CUtensorMap& wmap, const GemmParams& p, int n_tiles, cudaStream_t st) {
-    switch (gemm_variant()) {
-        case 1: return launch_gemm_var<FMT, T, BPAD, 1>(xmap, wmap, p, n_tiles, st);
-        default: return launch_gemm_var<FMT, T, BPAD, 0>(xmap, wmap, p, n_tiles, st);
-    }
+    return launch_gemm_var<FMT, T, BPAD, 0>(xmap, wmap, p, n_tiles, st);
 }
 
 template <int FMT, typename T>
@@ -470,10 +467,13 @@ int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const
     p.silu_mul = (flags & B200_GEMM_SILU_MUL) ? 1 : 0;
     ARG_CHECK(!p.silu_mul || N % 128 == 0, "wo_gemm: SILU_MUL needs N %% 128 == 0 (gate/up interleaved in 64-feature halves)");
     p.dbg = env_int("B200_GEMM_DBG", 0);
+#ifdef B200_GEMM_DEV
     {
-        const char* tr = getenv("B200_GEMM_TRACE_PTR");   // developer timeline buffer (device pointer, 8*64 int64)
+        const char* tr = getenv("B200_GEMM_TRACE_PTR");   // developer timeline buffer (device pointer)
         p.trace = (tr && *tr) ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 0)) : nullptr;
     }
+    p.dbg = env_int("B200_GEMM_DBG", 0);
+#endif
     p.cluster_reduce = env_int("B200_GEMM_CLUSTER", 1) ? 1 : 0;   // split-K merge through DSMEM (cluster <= 8) vs global semaphores
     gemm_split(n_tiles, p.k_blocks, p.cluster_reduce ? 8 : 16, &p.nsplit, &p.kb_per_split);
     if (p.silu_mul && !p.cluster_reduce) {

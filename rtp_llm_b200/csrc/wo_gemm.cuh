@@ -38,10 +38,9 @@ __host__ __device__ constexpr int gemm_w_bytes(int fmt) {
 // Shared-memory rings.  The weight ring (HBM stream) and the activation ring (L2 hits) are SEPARATE: a weight stage is
 // released as soon as the dequant warps hold its nibbles in registers, so its lifetime is one TMA latency, not the
 // whole dequant -> TMEM -> MMA chain, and the bytes in flight per SM (Little's law: ~44 GB/s * latency) stay high.
-// Variants (env B200_GEMM_VARIANT): 0 = one group of 8 dequant warps; 1 = two groups of 8 that take alternate k-blocks
-// (two blocks in flight per CTA: the per-block chain wait -> LDS -> math -> TMEM store -> publish is latency-bound).
-constexpr int kGemmVariants = 2;
-__host__ __device__ constexpr int gemm_ndq_warps(int var) { return var == 1 ? 16 : 8; }
+// 8 dequant warps = two groups of four taking alternate k-blocks (see the dequant section of the kernel).
+constexpr int kGemmVariants = 1;
+__host__ __device__ constexpr int gemm_ndq_warps(int var) { (void)var; return 8; }
 __host__ __device__ constexpr int gemm_threads(int var) { return (gemm_ndq_warps(var) + 3) * 32; }
 __host__ __device__ constexpr int gemm_x_stage_bytes(int bpad) { return bpad * 256; }
 __host__ __device__ constexpr int gemm_x_stages(int bpad) { return bpad <= 32 ? 4 : 3; }
@@ -185,12 +184,21 @@ struct Pair<__nv_bfloat16> {
     }
 };
 
-// developer timeline: TRACE(slot, it) stores clock64() for CTA (0,0); slots: 0 w-issue, 1 x-issue, 2 dq wfull, 3 dq math done,
-// 4 dq aempty seen, 5 dq afull arrive (for it-1), 6 mma operands ready, 7 mma issued
+// developer timeline (only in -DB200_GEMM_DEV builds, see tools/gemm_trace.py): TRACE(slot, it) stores clock64() for CTA
+// (0,0); slots: 0 w-issue, 1 x-issue, 2 dq wfull, 3 dq math done, 4 dq aempty seen, 5 dq afull arrive (for it-1),
+// 6 mma operands ready, 7 mma issued
+#ifdef B200_GEMM_DEV
 #define B200_TRACE(slot, it)                                                                     \
     do {                                                                                         \
         if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (it) < 64) p.trace[(slot) * 64 + (it)] = clock64(); \
     } while (0)
+#define B200_DBG(bit) (p.dbg & (bit))
+#define B200_TRACING (p.trace != nullptr)
+#else
+#define B200_TRACE(slot, it) do { } while (0)
+#define B200_DBG(bit) 0
+#define B200_TRACING false
+#endif
 
 template <int FMT, typename T, int BPAD, int VAR>
 __global__ void __launch_bounds__(gemm_threads(VAR), gemm_min_ctas(FMT, BPAD, VAR))
@@ -200,8 +208,6 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
     constexpr int NDQ_WARPS = gemm_ndq_warps(VAR);
     constexpr int NDQ_THREADS = NDQ_WARPS * 32;
     constexpr int W_WTMA = NDQ_WARPS, W_XTMA = NDQ_WARPS + 1, W_MMA = NDQ_WARPS + 2;
-    constexpr int GROUPS = NDQ_WARPS / 8;                  // dequant warp groups; group g owns k-blocks it % GROUPS == g
-    constexpr int CPW = 2;                                 // 32-k chunks of a k-block handled by one warp
     constexpr int X_BYTES = gemm_x_stage_bytes(BPAD);
     constexpr int W_BYTES = gemm_w_bytes(FMT);
     constexpr int A_STAGES = gemm_a_stages(BPAD, VAR);
@@ -211,8 +217,11 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
     constexpr uint32_t IDESC = make_idesc_f16(kGemmTileN, BPAD, kBf16);
     static_assert(WS >= 3, "weight ring too shallow");
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment is required by the 128B-swizzled tiles. The array is DECLARED aligned (the kernel has no static
+    // shared memory, so the dynamic segment starts at the aligned window base) and checked once; keeping the pointer's
+    // shared-space provenance lets nvcc emit LDS/STS instead of generic accesses with 64-bit address math.
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
     uint8_t* xring = smem;                                 // XS stages of [2 boxes][BPAD rows][128 B], SW128
     uint8_t* wring = smem + XS * X_BYTES;                  // WS stages of one weight block each
     uint64_t* wfull = reinterpret_cast<uint64_t*>(wring + WS * W_BYTES);   // W_BYTES is a multiple of 512
@@ -227,7 +236,7 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x, split = blockIdx.y;
-    if (p.trace && threadIdx.x == 0) {
+    if (B200_TRACING && threadIdx.x == 0) {
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         atomicMin(reinterpret_cast<unsigned long long*>(&p.trace[8 * 64 + 14]), gt);   // earliest CTA start (ns)
@@ -253,14 +262,14 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
     if (threadIdx.x == 0) {
         for (int s = 0; s < WS; ++s) {
             mbar_init(&wfull[s], 1);
-            mbar_init(&wempty[s], FMT == kFmtF16 ? 1 : 8);
+            mbar_init(&wempty[s], FMT == kFmtF16 ? 1 : 4);
         }
         for (int s = 0; s < XS; ++s) {
             mbar_init(&xfull[s], 1);
             mbar_init(&xempty[s], 1);
         }
         for (int a = 0; a < A_STAGES; ++a) {
-            mbar_init(&afull[a], 8);
+            mbar_init(&afull[a], 4);
             mbar_init(&aempty[a], 1);
         }
         mbar_init(dfull, 1);
@@ -333,25 +342,15 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
         if (p.use_pdl && lane == 0) pdl_launch_dependents();
         int sw = 0, sx = 0, a = 0;
         uint32_t phw = 0, phx = 0, aph = 0;
-        bool x_ready = false, o_ready = false;
         for (int it = 0; it < nkb; ++it) {
-            if (!x_ready) mbar_wait(&xfull[sx], phx);
-            if (!o_ready) {
-                if (FMT == kFmtF16) mbar_wait(&wfull[sw], phw);
-                else mbar_wait(&afull[a], aph);
-            }
-            // ring positions of the next block; probe them now, the answers come back while this block's MMAs issue
+            mbar_wait(&xfull[sx], phx);
+            if (FMT == kFmtF16) mbar_wait(&wfull[sw], phw);
+            else mbar_wait(&afull[a], aph);
             int sx_n = sx + 1, sw_n = sw + 1, a_n = a + 1;
             uint32_t phx_n = phx, phw_n = phw, aph_n = aph;
             if (sx_n == XS) { sx_n = 0; phx_n ^= 1; }
             if (sw_n == WS) { sw_n = 0; phw_n ^= 1; }
             if (a_n == A_STAGES) { a_n = 0; aph_n ^= 1; }
-            if (!(p.dbg & 16)) {
-                x_ready = o_ready = false;
-            } else if (it + 1 < nkb) {
-                x_ready = __all_sync(0xffffffffu, mbar_test(&xfull[sx_n], phx_n));
-                o_ready = __all_sync(0xffffffffu, (FMT == kFmtF16) ? mbar_test(&wfull[sw_n], phw_n) : mbar_test(&afull[a_n], aph_n));
-            }
             tc_fence_after();
             if (elect_one()) {
                 B200_TRACE(6, it);
@@ -359,7 +358,7 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
                 const uint32_t wsm = smem_u32(wring + sw * W_BYTES);
 #pragma unroll
                 for (int j = 0; j < kGemmBK / 16; ++j) {
-                    if (p.dbg & 4) break;
+                    if (B200_DBG(4)) break;
                     const uint64_t bdesc = make_smem_desc_sw128(xs + (j >> 2) * (BPAD * 128) + (j & 3) * 32);
                     const uint32_t acc = (it > 0 || j >= NACC) ? 1u : 0u;
                     const uint32_t dcol = tmem_d + (j % NACC) * BPAD;
@@ -383,108 +382,101 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
         }
     } else {
         // ------------------------------------------------------------------ dequant warps (TMEM A producers)
+        // Two groups of four warps take ALTERNATE k-blocks (two blocks in flight per CTA); inside a group warp q owns TMEM
+        // lane quarter q, i.e. 32 feature rows x the whole 128-deep block, processed as two 64-k halves. One barrier round
+        // (weights landed / TMEM buffer free / buffer published) therefore covers 4096 weights per warp: the round's
+        // latency (~100 cycles per mbarrier operation even when the phase is already complete) is what bounds this loop.
         const int quarter = warp & 3;     // TMEM lane quarter this warp may touch (hardware rule: warp id % 4)
-        const int grp = warp >> 3;        // dequant group
-        const int kc = (warp >> 2) & 1;   // which half (two 32-k chunks) of the k-block
+        const int grp = warp >> 2;        // dequant group 0/1
         const int row = quarter * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         if (FMT != kFmtF16) {
+            constexpr int G = 2;
             int s = grp % WS, a = grp % A_STAGES, a_prev = 0;
             uint32_t ph = 0, aph = 0;
             bool first = true;
-            // barrier probes are issued one step ahead (test_wait is ~150 cycles even when the phase is complete): the
-            // answer for the weight stage of block it+GROUPS and for this block's TMEM buffer arrive under the math.
-            bool w_ready = false;
-            for (int it = grp; it < nkb; it += GROUPS) {
-                if (!w_ready) mbar_wait(&wfull[s], ph);
+            for (int it = grp; it < nkb; it += G) {
+                mbar_wait(&wfull[s], ph);
                 if (threadIdx.x == 0) B200_TRACE(2, it);
-                const uint8_t* wb = wring + s * W_BYTES;
-                uint32_t regs[CPW][16];
-                bool a_free = false;
-                int s_n = s + GROUPS;
-                uint32_t ph_n = ph;
-                if (s_n >= WS) {
-                    s_n -= WS;
-                    ph_n ^= 1;
-                }
-#define PROBE_NEXT()                                                              \
-    do {                                                                          \
-        if (!(p.dbg & 16)) {   /* measured: probing ahead costs more than it hides; kept as experiment 16 */ \
-            a_free = false;                                                       \
-            w_ready = false;                                                      \
-            break;                                                                \
-        }                                                                         \
-        a_free = __all_sync(0xffffffffu, mbar_test(&aempty[a], aph ^ 1));         \
-        w_ready = (it + GROUPS < nkb) ? __all_sync(0xffffffffu, mbar_test(&wfull[s_n], ph_n)) : true; \
-    } while (0)
+                const uint32_t wb = smem_u32(wring) + s * W_BYTES;   // 32-bit shared address of this stage
+                typename Pair<T>::type s2, zs2;
                 if (FMT == kFmtInt4) {
-                    const uint16_t* sc = reinterpret_cast<const uint16_t*>(wb + 8192);
-                    const typename Pair<T>::type s2 = Pair<T>::bcast(sc[row]);
-                    const typename Pair<T>::type zs2 = Pair<T>::bcast(sc[128 + row]);
-                    uint4 v[CPW];
+                    s2 = Pair<T>::bcast((uint16_t)lds_u16(wb + 8192 + row * 2));
+                    zs2 = Pair<T>::bcast((uint16_t)lds_u16(wb + 8192 + 256 + row * 2));
+                }
 #pragma unroll
-                    for (int cc = 0; cc < CPW; ++cc)
-                        v[cc] = *reinterpret_cast<const uint4*>(wb + (kc * CPW + cc) * 2048 + row * 16);
-                    // the packed words are in registers: release the smem stage before doing the math
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&wempty[s]);
-                    PROBE_NEXT();
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t regs[2][16];
+                    if (FMT == kFmtInt4) {
+                        uint4 v[2];
 #pragma unroll
-                    for (int cc = 0; cc < CPW; ++cc) {
-                        if (p.dbg & 1) {
-#pragma unroll
-                            for (int q = 0; q < 16; ++q) regs[cc][q] = (q & 1) ? v[cc].x ^ v[cc].w : v[cc].y ^ v[cc].z;
-                            continue;
+                        for (int cc = 0; cc < 2; ++cc) v[cc] = lds_v4(wb + (half * 2 + cc) * 2048 + row * 16);
+                        if (half == 1) {   // every byte of the stage this warp needs is in registers: release it
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&wempty[s]);
                         }
-                        Dequant4<T>::word(v[cc].x, s2, zs2, &regs[cc][0]);
-                        Dequant4<T>::word(v[cc].y, s2, zs2, &regs[cc][4]);
-                        Dequant4<T>::word(v[cc].z, s2, zs2, &regs[cc][8]);
-                        Dequant4<T>::word(v[cc].w, s2, zs2, &regs[cc][12]);
+#pragma unroll
+                        for (int cc = 0; cc < 2; ++cc) {
+                            if (B200_DBG(1)) {
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) regs[cc][q] = (q & 1) ? v[cc].x ^ v[cc].w : v[cc].y ^ v[cc].z;
+                                continue;
+                            }
+                            Dequant4<T>::word(v[cc].x, s2, zs2, &regs[cc][0]);
+                            Dequant4<T>::word(v[cc].y, s2, zs2, &regs[cc][4]);
+                            Dequant4<T>::word(v[cc].z, s2, zs2, &regs[cc][8]);
+                            Dequant4<T>::word(v[cc].w, s2, zs2, &regs[cc][12]);
+                        }
+                    } else {
+                        uint4 v[2][2];
+#pragma unroll
+                        for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) v[cc][h] = lds_v4(wb + ((half * 2 + cc) * 2 + h) * 2048 + row * 16);
+                        if (half == 1) {
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&wempty[s]);
+                        }
+#pragma unroll
+                        for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                Dequant8<T>::word(v[cc][h].x, &regs[cc][h * 8 + 0]);
+                                Dequant8<T>::word(v[cc][h].y, &regs[cc][h * 8 + 2]);
+                                Dequant8<T>::word(v[cc][h].z, &regs[cc][h * 8 + 4]);
+                                Dequant8<T>::word(v[cc][h].w, &regs[cc][h * 8 + 6]);
+                            }
                     }
-                } else {
-                    uint4 v[CPW][2];
-#pragma unroll
-                    for (int cc = 0; cc < CPW; ++cc)
-#pragma unroll
-                        for (int h = 0; h < 2; ++h)
-                            v[cc][h] = *reinterpret_cast<const uint4*>(wb + ((kc * CPW + cc) * 2 + h) * 2048 + row * 16);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&wempty[s]);
-                    PROBE_NEXT();
-#pragma unroll
-                    for (int cc = 0; cc < CPW; ++cc)
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            Dequant8<T>::word(v[cc][h].x, &regs[cc][h * 8 + 0]);
-                            Dequant8<T>::word(v[cc][h].y, &regs[cc][h * 8 + 2]);
-                            Dequant8<T>::word(v[cc][h].z, &regs[cc][h * 8 + 4]);
-                            Dequant8<T>::word(v[cc][h].w, &regs[cc][h * 8 + 6]);
+                    if (half == 0) {
+                        if (threadIdx.x == 0) B200_TRACE(3, it);
+                        // software pipeline: this group's PREVIOUS block had a whole half of math to land in TMEM; publish it
+                        if (!first) {
+                            tmem_wait_st();
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&afull[a_prev]);
+                            if (threadIdx.x == 0) B200_TRACE(5, it);
                         }
-                }
-                if (threadIdx.x == 0) B200_TRACE(3, it);
-                // software pipeline: the PREVIOUS block's TMEM stores had this block's math to complete; publish them now
-                if (!first) {
-                    tmem_wait_st();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&afull[a_prev]);
-                    if (threadIdx.x == 0) B200_TRACE(5, it);
-                }
-                first = false;
-                if (!a_free) mbar_wait(&aempty[a], aph ^ 1);
-                if (threadIdx.x == 0) B200_TRACE(4, it);
-                tc_fence_after();
-                const uint32_t dst = tmem_a + lane_addr + a * 64 + kc * CPW * 16;
-                if (p.dbg & 2) {
-                    if (regs[0][0] == 0x12345678u && regs[CPW - 1][15] == 0x9abcdef0u) s_flag[1] = 1;  // keep the math alive
-                } else {
-#pragma unroll
-                    for (int cc = 0; cc < CPW; ++cc) tmem_st_32x32b_x16(dst + cc * 16, regs[cc]);
+                        first = false;
+                        mbar_wait(&aempty[a], aph ^ 1);
+                        if (threadIdx.x == 0) B200_TRACE(4, it);
+                        tc_fence_after();
+                    }
+                    const uint32_t dst = tmem_a + lane_addr + a * 64 + half * 32;
+                    if (B200_DBG(2)) {
+                        if (regs[0][0] == 0x12345678u && regs[1][15] == 0x9abcdef0u) s_flag[1] = 1;  // keep the math alive
+                    } else {
+                        tmem_st_32x32b_x16(dst, regs[0]);
+                        tmem_st_32x32b_x16(dst + 16, regs[1]);
+                    }
                 }
                 a_prev = a;
-                s = s_n;
-                ph = ph_n;
-                a += GROUPS;
+                s += G;
+                if (s >= WS) {
+                    s -= WS;
+                    ph ^= 1;
+                }
+                a += G;
                 if (a >= A_STAGES) {
                     a -= A_STAGES;
                     aph ^= 1;
@@ -501,7 +493,7 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
         // ------------------------------------------------------------------ epilogue
 #define B200_TRACE_E(i)                                                                                          \
     do {                                                                                                         \
-        if (p.trace && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) p.trace[8 * 64 + 8 + (i)] = clock64(); \
+        if (B200_TRACING && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) p.trace[8 * 64 + 8 + (i)] = clock64(); \
     } while (0)
         B200_TRACE_E(0);
         mbar_wait(dfull, 0);
@@ -658,7 +650,7 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
         }
     }
     __syncthreads();
-    if (p.trace && threadIdx.x == 0) {
+    if (B200_TRACING && threadIdx.x == 0) {
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         atomicMax(reinterpret_cast<unsigned long long*>(&p.trace[8 * 64 + 15]), gt);   // latest CTA end (ns)

@@ -117,17 +117,14 @@ if __name__ == "__main__":
         bench_attn(64, 32, 8, 4096)
         bench_attn(16, 8, 1, 8192)
     if "gemm" in which:
-        for rep in range(2):
-            for dbg in (0, 16):
-                print(f"--- rep {rep} B200_GEMM_DBG={dbg} (16 = barrier probes off)")
-                os.environ["B200_GEMM_DBG"] = str(dbg)
-                bench_gemm(B200_FMT_INT4, 32, 4096, 6144)
-                bench_gemm(B200_FMT_INT4, 32, 4096, 4096)
-                bench_gemm(B200_FMT_INT4, 32, 4096, 28672)
-                bench_gemm(B200_FMT_INT4, 32, 14336, 4096)
-                bench_gemm(B200_FMT_INT8, 32, 4096, 28672)
-        os.environ["B200_GEMM_DBG"] = "0"
-        for s_ in (2, 4, 8):
-            bench_gemm(B200_FMT_INT4, 32, 4096, 6144, env={"B200_GEMM_SPLITK": s_})
-            bench_gemm(B200_FMT_INT4, 32, 14336, 4096, env={"B200_GEMM_SPLITK": s_})
+        for B in (32,):
+            bench_gemm(B200_FMT_INT4, B, 4096, 6144)
+            bench_gemm(B200_FMT_INT4, B, 4096, 4096)
+            bench_gemm(B200_FMT_INT4, B, 4096, 28672)
+            bench_gemm(B200_FMT_INT4, B, 14336, 4096)
+        bench_gemm(B200_FMT_INT4, 32, 4096, 28672, pdl=True)
+        bench_gemm(B200_FMT_INT4, 1, 4096, 28672)
+        bench_gemm(B200_FMT_INT4, 64, 4096, 28672)
+        bench_gemm(B200_FMT_INT8, 32, 4096, 28672)
+        bench_gemm(B200_FMT_F16, 32, 4096, 28672)
         bench_gemm(B200_FMT_F16, 32, 4096, 128256)
