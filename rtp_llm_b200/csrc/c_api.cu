@@ -220,11 +220,6 @@ int launch_gemm_var(const CUtensorMap& xmap, const CUtensorMap& wmap, const Gemm
     return launched("wo_gemm_kernel");
 }
 
-int gemm_variant() {
-    int v = env_int("B200_GEMM_VARIANT", 0);   // read per call: cheap, and lets one process compare variants
-    if (v < 0 || v >= kGemmVariants) v = 0;
-    return v;
-}
 template <int FMT, typename T, int BPAD>
 int launch_gemm(const CUtensorMap& xmap, const CUtensorMap& wmap, const GemmParams& p, int n_tiles, cudaStream_t st) {
     return launch_gemm_var<FMT, T, BPAD, 0>(xmap, wmap, p, n_tiles, st);
