@@ -595,8 +595,8 @@ int b200_argmax(const void* logits, int dtype, int rows, int vocab, int32_t* out
 
 // ------------------------------------------------------------------------------------------------ peer all-reduce
 size_t b200_peer_ar_region_bytes(size_t max_message_bytes) {
-    // [2 data slots][flags W x CTAs][epochs]
-    return 2 * round_up(max_message_bytes, 256) + kArMaxWorld * kArMaxCtas * sizeof(uint32_t) + kArMaxCtas * sizeof(uint32_t) + 256;
+    // [2 parities][W sources][LL slot = 2 x message] + per-CTA epochs
+    return 2 * (size_t)kArMaxWorld * 2 * round_up(max_message_bytes, 256) + kArMaxCtas * sizeof(uint32_t) + 256;
 }
 
 int b200_peer_alloc(size_t bytes, void** ptr, void* ipc_handle_out /*64 bytes*/) {
@@ -629,23 +629,22 @@ int b200_peer_allreduce(const void* in, void* out, size_t bytes, int is_bf16, vo
     ARG_CHECK(world >= 2 && world <= kArMaxWorld && rank >= 0 && rank < world, "peer_allreduce: bad rank/world %d/%d", rank, world);
     ARG_CHECK(bytes > 0 && bytes % 16 == 0 && bytes <= max_message_bytes, "peer_allreduce: message of %zu bytes unsupported", bytes);
     ARG_CHECK((((uintptr_t)in | (uintptr_t)out) & 15) == 0, "peer_allreduce: in/out must be 16-byte aligned");
-    const size_t slot_b = round_up(max_message_bytes, 256);
+    const size_t src_stride = 2 * round_up(max_message_bytes, 256);          // LL doubles the bytes
+    const size_t parity_stride = (size_t)kArMaxWorld * src_stride;
     PeerArParams p{};
     p.in = in;
     p.out = out;
     for (int r = 0; r < world; ++r) {
         uint8_t* base = reinterpret_cast<uint8_t*>(regions[r]);
         ARG_CHECK(base, "peer_allreduce: region %d is null", r);
-        p.slot[r] = base + (call_parity & 1) * slot_b;
-        p.flags[r] = reinterpret_cast<uint32_t*>(base + 2 * slot_b);
+        p.slots[r] = base + (size_t)(call_parity & 1) * parity_stride;
     }
-    p.epoch = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(regions[rank]) + 2 * slot_b +
-                                          kArMaxWorld * kArMaxCtas * sizeof(uint32_t));
+    p.epoch = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(regions[rank]) + 2 * parity_stride);
+    p.src_stride = src_stride;
     p.n16 = (int)(bytes / 16);
     p.rank = rank;
     p.world = world;
-    int ctas = (p.n16 + 4 * kArThreads - 1) / (4 * kArThreads);   // >= 4 chunks (64 B) per thread: fewer flags to exchange
-    if (ctas > kArMaxCtas) ctas = kArMaxCtas;
+    int ctas = (p.n16 + 2 * kArThreads - 1) / (2 * kArThreads);   // ~2 chunks (32 B of payload) per thread
     if (ctas < 1) ctas = 1;
     ctas = env_int("B200_AR_CTAS", ctas);
     if (ctas > kArMaxCtas) ctas = kArMaxCtas;

@@ -1,10 +1,13 @@
 // One-shot SUM all-reduce of a small [rows][hidden] fp16/bf16 tensor over NVLink peer memory, for the TP all-reduce after
 // the row-parallel GEMMs (reference: rtp_llm/models_py/distributed/collective_torch.py:694-722; its fast path is torch
-// symmetric memory one-/two-shot + multimem, symm_mem.py:126-185). 256 KiB messages are latency-bound: every rank copies
-// its contribution into its own peer-visible slot, raises one flag per (peer, CTA), then reads all W slots over NVLink
-// and sums them in rank order 0..W-1 -- the same order on every rank, so all ranks produce bit-identical results.
-// No second barrier: two slots alternate between consecutive calls, and a peer can only raise its flag for call k+1
-// after it has finished reading call k (stream order), so slot (k & 1) is free again when call k+2 writes it.
+// symmetric memory one-/two-shot + multimem, symm_mem.py:126-185). 256 KiB messages are pure latency, so the exchange is
+// PUSH-based with the flag travelling inside the data ("LL" style): every rank writes its contribution, as 8-byte
+// {data32, epoch32} words, straight into a per-source slot of every peer's region, then polls its OWN memory until all
+// sources carry the current epoch and sums them in rank order 0..W-1 (same order everywhere -> bit-identical results on all
+// ranks). One NVLink traversal, no separate barrier, no remote reads.
+// Slot reuse: two parity slots alternate between consecutive calls; a peer can only start call k+2 after it completed
+// call k+1, which needed this rank's call-k+1 data, which this rank sends only after finishing call k -- so the slot of
+// call k is no longer being read when call k+2 overwrites it.
 #pragma once
 #include "ptx.cuh"
 
@@ -17,43 +20,32 @@ constexpr int kArThreads = 256;
 struct PeerArParams {
     const void* in;                 // local contribution [n16 * 16 bytes]
     void* out;                      // local result (may alias `in`)
-    uint8_t* slot[kArMaxWorld];     // peer-visible data slot of every rank for THIS call (rank r's own entry is local memory)
-    uint32_t* flags[kArMaxWorld];   // flags[r] = rank r's flag array [kArMaxWorld][kArMaxCtas] (we write ours into row `rank`)
-    uint32_t* epoch;                // local [kArMaxCtas] call counters, one per CTA (graph-replay safe: advanced in-kernel)
-    int n16;                        // number of 16-byte chunks
+    uint8_t* slots[kArMaxWorld];    // slots[r]: base of rank r's receive area for THIS call parity: [src W][n16_max * 32 bytes]
+    uint32_t* epoch;                // local [kArMaxCtas] call counters, one per CTA (advanced in-kernel: graph-replay safe)
+    size_t src_stride;              // bytes between the per-source slots
+    int n16;                        // number of 16-byte payload chunks
     int rank, world;
 };
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_ll(uint8_t* p, uint32_t data, uint32_t flag) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(flag) : "memory");
 }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// peer lines may sit stale in the local L1 from two calls ago (same slot): volatile loads always go to the owner
-__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
+__device__ __forceinline__ uint4 ld_ll2(const uint8_t* p) {   // two LL words: {d0, f0, d1, f1}
     uint4 v;
     asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
 
 template <typename T>
-__device__ __forceinline__ void acc8(float (&a)[8], const uint4& v) {
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        if (sizeof(T) == 2 && std::is_same<T, __half>::value) {
-            float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-            a[2 * i] += f.x;
-            a[2 * i + 1] += f.y;
-        } else {
-            float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
-            a[2 * i] += f.x;
-            a[2 * i + 1] += f.y;
-        }
+__device__ __forceinline__ void acc2(float& a0, float& a1, uint32_t w) {
+    if (std::is_same<T, __half>::value) {
+        float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+        a0 += f.x;
+        a1 += f.y;
+    } else {
+        float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+        a0 += f.x;
+        a1 += f.y;
     }
 }
 
@@ -65,33 +57,47 @@ __global__ void __launch_bounds__(kArThreads) peer_allreduce_kernel(const PeerAr
     const int per = (p.n16 + nctas - 1) / nctas;
     const int c0 = cta * per, c1 = min(c0 + per, p.n16);
     const uint32_t epoch = p.epoch[cta] + 1;
-
-    // 1) publish this CTA's chunk range in the local peer-visible slot
     const uint4* src = reinterpret_cast<const uint4*>(p.in);
-    uint4* mine = reinterpret_cast<uint4*>(p.slot[p.rank]);
-    for (int i = c0 + threadIdx.x; i < c1; i += kArThreads) mine[i] = src[i];
-    __syncthreads();
-    // 2) one flag per (peer, CTA): "rank `rank`, CTA `cta` has published call `epoch`". The release store of a thread that
-    //    passed the CTA barrier is cumulative over the other threads' stores -- no per-thread system fence needed.
-    if (threadIdx.x < p.world) st_release_sys(p.flags[threadIdx.x] + p.rank * kArMaxCtas + cta, epoch);
-    // 3) wait until every rank's matching CTA has published
-    if (threadIdx.x < p.world) {
-        const uint32_t* f = p.flags[p.rank] + threadIdx.x * kArMaxCtas + cta;
-        while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+
+    // 1) push: my chunk range goes into slot [src = rank] of every peer, each 32-bit word tagged with the epoch
+    for (int i = c0 + threadIdx.x; i < c1; i += kArThreads) {
+        const uint4 v = src[i];
+#pragma unroll
+        for (int r = 0; r < kArMaxWorld; ++r) {
+            if (r < p.world && r != p.rank) {
+                uint8_t* dst = p.slots[r] + (size_t)p.rank * p.src_stride + (size_t)i * 32;
+                st_ll(dst, v.x, epoch);
+                st_ll(dst + 8, v.y, epoch);
+                st_ll(dst + 16, v.z, epoch);
+                st_ll(dst + 24, v.w, epoch);
+            }
         }
     }
-    __syncthreads();
-    // 4) sum the W slots in rank order (identical on every rank)
+    // 2) pull from my own memory: wait for every source's words of this epoch, sum in rank order
     uint4* dst = reinterpret_cast<uint4*>(p.out);
     for (int i = c0 + threadIdx.x; i < c1; i += kArThreads) {
-        uint4 v[kArMaxWorld];
-#pragma unroll
-        for (int r = 0; r < kArMaxWorld; ++r)
-            if (r < p.world) v[r] = ld_volatile_v4(reinterpret_cast<const uint4*>(p.slot[r]) + i);
+        const uint4 mine = src[i];
         float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int r = 0; r < kArMaxWorld; ++r)
-            if (r < p.world) acc8<T>(a, v[r]);
+        for (int r = 0; r < kArMaxWorld; ++r) {
+            if (r >= p.world) continue;
+            uint32_t w0, w1, w2, w3;
+            if (r == p.rank) {
+                w0 = mine.x; w1 = mine.y; w2 = mine.z; w3 = mine.w;
+            } else {
+                const uint8_t* q = p.slots[p.rank] + (size_t)r * p.src_stride + (size_t)i * 32;
+                uint4 lo, hi;
+                do {
+                    lo = ld_ll2(q);
+                    hi = ld_ll2(q + 16);
+                } while (lo.y != epoch || lo.w != epoch || hi.y != epoch || hi.w != epoch);
+                w0 = lo.x; w1 = lo.z; w2 = hi.x; w3 = hi.z;
+            }
+            acc2<T>(a[0], a[1], w0);
+            acc2<T>(a[2], a[3], w1);
+            acc2<T>(a[4], a[5], w2);
+            acc2<T>(a[6], a[7], w3);
+        }
         uint4 o;
         o.x = pack2<T>(a[0], a[1]);
         o.y = pack2<T>(a[2], a[3]);
@@ -99,6 +105,7 @@ __global__ void __launch_bounds__(kArThreads) peer_allreduce_kernel(const PeerAr
         o.w = pack2<T>(a[6], a[7]);
         dst[i] = o;
     }
+    __syncthreads();
     if (threadIdx.x == 0) p.epoch[cta] = epoch;
 }
 

@@ -28,7 +28,7 @@ class PeerComm(NcclComm):
     cudaMalloc's a peer-visible region, the 64-byte IPC handles travel over the existing process group, and the kernel
     reads all peers' slots directly. The (once per step, 2 MB) logits all-gather stays on NCCL."""
 
-    MAX_MESSAGE = 1 << 20   # decode all-reduces are [B, hidden] fp16: 256 KiB at the BASELINE configs
+    MAX_MESSAGE = 1 << 19   # decode all-reduces are [B, hidden] fp16: 256 KiB at the BASELINE configs (region = 16 MiB)
 
     def __init__(self, device: torch.device, group=None):
         super().__init__(device, group)
