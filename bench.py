@@ -123,7 +123,7 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.p = None

@@ -277,6 +277,12 @@ def glue_cases():
         lg[2, 10] = lg[2, 500] = 99.0
         am = ops.argmax(lg)
         report("argmax fp32", bool((am.cpu().numpy() == orc.argmax(lg.cpu().numpy())).all()))
+        for dt in (torch.float16, torch.bfloat16):
+            lh = lg.to(dt)                                   # rounding creates many exact ties: lowest index must win
+            ah = ops.argmax(lh)
+            report(f"argmax {dt} (vectorised path, ties)", bool((ah.cpu().numpy() == orc.argmax(lh.float().cpu().numpy())).all()))
+            lo = lh[:, :1001].contiguous()                   # vocab % 8 != 0 -> scalar path
+            report(f"argmax {dt} (scalar path)", bool((ops.argmax(lo).cpu().numpy() == orc.argmax(lo.float().cpu().numpy())).all()))
         tbl = torch.randn(1000, 4096, device=dev).half()
         ids = torch.tensor([3, 999, 0], dtype=torch.int32, device=dev)
         report("embedding", bool((ops.embedding(ids, tbl) == tbl[ids.long()]).all()))
