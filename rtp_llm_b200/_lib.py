@@ -4,7 +4,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_size_t, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200_decode.so")
+LIB_PATH = os.environ.get("B200_LIB_PATH") or os.path.join(HERE, "libb200_decode.so")   # override: developer A/B builds
 
 B200_FMT_F16, B200_FMT_INT8, B200_FMT_INT4 = 0, 1, 2
 B200_GEMM_PDL = 1

@@ -43,7 +43,10 @@ constexpr int kGemmVariants = 1;
 __host__ __device__ constexpr int gemm_ndq_warps(int var) { (void)var; return 8; }
 __host__ __device__ constexpr int gemm_threads(int var) { return (gemm_ndq_warps(var) + 3) * 32; }
 __host__ __device__ constexpr int gemm_x_stage_bytes(int bpad) { return bpad * 256; }
-__host__ __device__ constexpr int gemm_x_stages(int bpad) { return bpad <= 32 ? 4 : 3; }
+#ifndef B200_GEMM_XS
+#define B200_GEMM_XS 4
+#endif
+__host__ __device__ constexpr int gemm_x_stages(int bpad) { return bpad <= 32 ? B200_GEMM_XS : 3; }
 constexpr int kGemmSmemMisc = 1024 /*align*/ + 1024 /*barriers*/;
 __host__ __device__ constexpr int gemm_w_stages_for(int fmt, int bpad, int budget) {
     int n = (budget - kGemmSmemMisc - gemm_x_stages(bpad) * gemm_x_stage_bytes(bpad)) / gemm_w_bytes(fmt);
@@ -229,7 +232,11 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
     uint64_t* xfull = wempty + WS;
     uint64_t* xempty = xfull + XS;
     uint64_t* afull = xempty + XS;                         // TMEM A buffer written
+#ifdef B200_GEMM_HALF_PUBLISH   // experiment (measured: no gain): publish the two 64-k halves of a TMEM buffer separately
+    uint64_t* aempty = afull + 2 * A_STAGES;               // afull[a] = first 64 k of buffer a, afull[A_STAGES + a] = second 64 k
+#else
     uint64_t* aempty = afull + A_STAGES;                   // TMEM A buffer consumed by the MMA
+#endif
     uint64_t* dfull = aempty + A_STAGES;                   // accumulator complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dfull + 1);
     int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
@@ -270,6 +277,9 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
         }
         for (int a = 0; a < A_STAGES; ++a) {
             mbar_init(&afull[a], 4);
+#ifdef B200_GEMM_HALF_PUBLISH
+            mbar_init(&afull[A_STAGES + a], 4);
+#endif
             mbar_init(&aempty[a], 1);
         }
         mbar_init(dfull, 1);
@@ -359,6 +369,12 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < kGemmBK / 16; ++j) {
                     if (B200_DBG(4)) break;
+#ifdef B200_GEMM_HALF_PUBLISH
+                    if (FMT != kFmtF16 && j == 4) {        // the second 64 k of the block are published separately
+                        mbar_wait(&afull[A_STAGES + a], aph);
+                        tc_fence_after();
+                    }
+#endif
                     const uint64_t bdesc = make_smem_desc_sw128(xs + (j >> 2) * (BPAD * 128) + (j & 3) * 32);
                     const uint32_t acc = (it > 0 || j >= NACC) ? 1u : 0u;
                     const uint32_t dcol = tmem_d + (j % NACC) * BPAD;
@@ -392,9 +408,8 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         if (FMT != kFmtF16) {
             constexpr int G = 2;
-            int s = grp % WS, a = grp % A_STAGES, a_prev = 0;
+            int s = grp % WS, a = grp % A_STAGES;
             uint32_t ph = 0, aph = 0;
-            bool first = true;
             for (int it = grp; it < nkb; it += G) {
                 mbar_wait(&wfull[s], ph);
                 if (threadIdx.x == 0) B200_TRACE(2, it);
@@ -449,15 +464,6 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
                     }
                     if (half == 0) {
                         if (threadIdx.x == 0) B200_TRACE(3, it);
-                        // software pipeline: this group's PREVIOUS block had a whole half of math to land in TMEM; publish it
-                        if (!first) {
-                            tmem_wait_st();
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&afull[a_prev]);
-                            if (threadIdx.x == 0) B200_TRACE(5, it);
-                        }
-                        first = false;
                         mbar_wait(&aempty[a], aph ^ 1);
                         if (threadIdx.x == 0) B200_TRACE(4, it);
                         tc_fence_after();
@@ -469,8 +475,23 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
                         tmem_st_32x32b_x16(dst, regs[0]);
                         tmem_st_32x32b_x16(dst + 16, regs[1]);
                     }
+#ifdef B200_GEMM_HALF_PUBLISH
+                    // publish each 64-k half on its own barrier: the MMA starts on half 0 while half 1 is being dequantised
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&afull[half * A_STAGES + a]);
+#endif
                 }
-                a_prev = a;
+#ifndef B200_GEMM_HALF_PUBLISH
+                // publish the block at once (measured: deferring the publish behind the next block's math is slower --
+                // the dequant -> MMA -> release chain, not the TMEM store latency, bounds the loop)
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&afull[a]);
+#endif
+                if (threadIdx.x == 0) B200_TRACE(5, it);
                 s += G;
                 if (s >= WS) {
                     s -= WS;
@@ -481,12 +502,6 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
                     a -= A_STAGES;
                     aph ^= 1;
                 }
-            }
-            if (!first) {
-                tmem_wait_st();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&afull[a_prev]);
             }
         }
 
