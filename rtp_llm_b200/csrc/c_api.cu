@@ -595,8 +595,8 @@ int b200_argmax(const void* logits, int dtype, int rows, int vocab, int32_t* out
 
 // ------------------------------------------------------------------------------------------------ peer all-reduce
 size_t b200_peer_ar_region_bytes(size_t max_message_bytes) {
-    // [2 parities][W sources][LL slot = 2 x message] + per-CTA epochs
-    return 2 * (size_t)kArMaxWorld * 2 * round_up(max_message_bytes, 256) + kArMaxCtas * sizeof(uint32_t) + 256;
+    // [2 parities][2 areas (one-shot / reduce-scatter, all-gather)][W sources][LL slot = 2 x message] + per-CTA epochs
+    return 2 * 2 * (size_t)kArMaxWorld * 2 * round_up(max_message_bytes, 256) + kArMaxCtas * sizeof(uint32_t) + 256;
 }
 
 int b200_peer_alloc(size_t bytes, void** ptr, void* ipc_handle_out /*64 bytes*/) {
@@ -630,7 +630,8 @@ int b200_peer_allreduce(const void* in, void* out, size_t bytes, int is_bf16, vo
     ARG_CHECK(bytes > 0 && bytes % 16 == 0 && bytes <= max_message_bytes, "peer_allreduce: message of %zu bytes unsupported", bytes);
     ARG_CHECK((((uintptr_t)in | (uintptr_t)out) & 15) == 0, "peer_allreduce: in/out must be 16-byte aligned");
     const size_t src_stride = 2 * round_up(max_message_bytes, 256);          // LL doubles the bytes
-    const size_t parity_stride = (size_t)kArMaxWorld * src_stride;
+    const size_t area_stride = (size_t)kArMaxWorld * src_stride;
+    const size_t parity_stride = 2 * area_stride;
     PeerArParams p{};
     p.in = in;
     p.out = out;
@@ -638,6 +639,7 @@ int b200_peer_allreduce(const void* in, void* out, size_t bytes, int is_bf16, vo
         uint8_t* base = reinterpret_cast<uint8_t*>(regions[r]);
         ARG_CHECK(base, "peer_allreduce: region %d is null", r);
         p.slots[r] = base + (size_t)(call_parity & 1) * parity_stride;
+        p.slots2[r] = p.slots[r] + area_stride;
     }
     p.epoch = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(regions[rank]) + 2 * parity_stride);
     p.src_stride = src_stride;
@@ -649,6 +651,20 @@ int b200_peer_allreduce(const void* in, void* out, size_t bytes, int is_bf16, vo
     ctas = env_int("B200_AR_CTAS", ctas);
     if (ctas > kArMaxCtas) ctas = kArMaxCtas;
     const bool pdl = g_pdl.load() != 0;
+    // W >= 3: reduce-scatter + all-gather (2 hops, (W-1)/W of the volume twice); W == 2: one hop. Env override for tests.
+    const int two_shot = env_int("B200_AR_TWOSHOT", world >= 3 ? 1 : 0) && (p.n16 % world == 0);
+    if (two_shot) {
+        int c2 = (p.n16 / world + kArThreads - 1) / kArThreads;
+        if (c2 < 1) c2 = 1;
+        if (c2 > kArMaxCtas) c2 = kArMaxCtas;
+        c2 = env_int("B200_AR_CTAS", c2);
+        if (c2 > kArMaxCtas) c2 = kArMaxCtas;
+        if (is_bf16)
+            CUDA_CHECK(launch_ex(peer_allreduce_twoshot_kernel<__nv_bfloat16>, dim3(c2), dim3(kArThreads), 0, (cudaStream_t)stream, pdl, p));
+        else
+            CUDA_CHECK(launch_ex(peer_allreduce_twoshot_kernel<__half>, dim3(c2), dim3(kArThreads), 0, (cudaStream_t)stream, pdl, p));
+        return launched("peer_allreduce_twoshot_kernel");
+    }
     if (is_bf16)
         CUDA_CHECK(launch_ex(peer_allreduce_kernel<__nv_bfloat16>, dim3(ctas), dim3(kArThreads), 0, (cudaStream_t)stream, pdl, p));
     else
