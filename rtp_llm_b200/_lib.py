@@ -53,8 +53,13 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise B200Error(f"{LIB_PATH} is missing: run `python -m rtp_llm_b200.build` (nvcc, sm_100a). "
-                            "There is no fallback path.")
+            # not a fallback: the only thing we ever do about a missing native library is build the native library
+            try:
+                from . import build as _build
+                _build.build()
+            except Exception as e:  # noqa: BLE001
+                raise B200Error(f"{LIB_PATH} is missing and could not be built ({e}): run `python -m rtp_llm_b200.build` "
+                                "(nvcc, sm_100a). There is no fallback path.") from e
         lib = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the header and the library ever diverge
