@@ -33,5 +33,34 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+PYBIND_SO = os.path.join(HERE, "b200_compute_ops.so")
+
+
+def build_pybind(force: bool = False) -> str:
+    """Compile csrc/pybind_ops.cc (registerPyModuleOps + the XQAAttnOp-shaped class) against torch's headers and link it to
+    libb200_decode.so. Plain g++ (no JIT cache): the .so stays in-tree and travels with the snapshot."""
+    src = os.path.join(CSRC, "pybind_ops.cc")
+    if not force and os.path.exists(PYBIND_SO) and os.path.getmtime(PYBIND_SO) > max(
+            os.path.getmtime(src), os.path.getmtime(os.path.join(HERE, "..", "include", "b200_decode_ops.h"))):
+        return PYBIND_SO
+    build()
+    import sysconfig
+    import torch
+    from torch.utils import cpp_extension as ce
+    inc = ce.include_paths() + [sysconfig.get_paths()["include"], "/usr/local/cuda/include"]
+    libdir = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden", "-DTORCH_EXTENSION_NAME=b200_compute_ops", "-DTORCH_API_INCLUDE_EXTENSION_H",
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}"] + [f"-I{i}" for i in inc] + \
+          [src, "-o", PYBIND_SO, f"-L{libdir}", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python",
+           f"-L{HERE}", "-l:libb200_decode.so", "-L/usr/local/cuda/lib64", "-lcudart",
+           f"-Wl,-rpath,{libdir}", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,/usr/local/cuda/lib64"]
+    subprocess.check_call(cmd)
+    return PYBIND_SO
+
+
 if __name__ == "__main__":
+    if "--pybind" in sys.argv:
+        print(build_pybind(force="--force" in sys.argv))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
