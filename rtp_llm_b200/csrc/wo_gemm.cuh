@@ -7,15 +7,16 @@
 //
 // B200 design (swap-AB, weights stationary on the MMA M side):
 //   * one CTA = 128 output features x a run of 128-deep k-blocks (split-K across blockIdx.y);
-//   * TMA warp : producer. Weights were re-laid out at load time into per-(n-tile,k-block) contiguous blobs
-//                (packed nibbles + the group's scales and zero*scale), so one cp.async.bulk stages a whole block;
-//                the activation block [B x 128] comes through a 128B-swizzled tensor map (OOB rows zero-filled);
+//   * two TMA warps: weights were re-laid out at load time into per-(n-tile,k-block) contiguous blobs (packed nibbles +
+//                the group's scales and zero*scale), so ONE cp.async.bulk stages a whole block (weight ring); the
+//                activation block [B x 128] comes through a 128B-swizzled tensor map, OOB rows zero-filled (activation ring);
 //   * dequant warps: dequantise IN REGISTERS (lop3 magic-number int->fp16, exact; hfma2 with the group scale / zero*scale)
 //                and store the fp16 operand straight INTO TENSOR MEMORY (tcgen05.st) -- the A operand of
 //   * MMA warp : one elected thread issues tcgen05.mma (M=128 features, N=batch pad, K=16) with A from TMEM and
 //                B (activations, K-major SW128) from shared memory, fp32 accumulators in TMEM;
-//   * epilogue : the dequant warps read the accumulators (tcgen05.ld), split-K partials are merged by the last-arriving CTA
-//                (fixed order -> deterministic), bias / per-column scale applied, coalesced stores.
+//   * epilogue : the dequant warps read the accumulators (tcgen05.ld); the split-K CTAs of a tile form a thread-block cluster
+//                and merge their fp32 partials through distributed shared memory in fixed order (deterministic); bias /
+//                per-column scale / optional fused SiLU(gate)*up applied; coalesced stores.
 //   The FP16-weight variant feeds A from shared memory (TMA tensor map, SW128) with the same pipeline.
 #pragma once
 #include <type_traits>
@@ -39,7 +40,6 @@ __host__ __device__ constexpr int gemm_w_bytes(int fmt) {
 // released as soon as the dequant warps hold its nibbles in registers, so its lifetime is one TMA latency, not the
 // whole dequant -> TMEM -> MMA chain, and the bytes in flight per SM (Little's law: ~44 GB/s * latency) stay high.
 // 8 dequant warps = two groups of four taking alternate k-blocks (see the dequant section of the kernel).
-constexpr int kGemmVariants = 1;
 __host__ __device__ constexpr int gemm_ndq_warps(int var) { (void)var; return 8; }
 __host__ __device__ constexpr int gemm_threads(int var) { return (gemm_ndq_warps(var) + 3) * 32; }
 __host__ __device__ constexpr int gemm_x_stage_bytes(int bpad) { return bpad * 256; }
