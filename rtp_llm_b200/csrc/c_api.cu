@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -128,16 +129,19 @@ void attn_split(int units, int max_tiles, int* nsplit, int* tiles_per_split) {
     int best_c = max_tiles;
     double best = 1e30;
     const int sms = num_sms();
-    // Measured on B200 (profiles/r01_kernel_bench.txt): a CTA costs ~2.5 tiles of fixed time (launch, Q load, pipeline
-    // fill, merge) and two CTAs are resident per SM, so: fewest waves of 2*SMs slots, then the largest chunk.
-    const long slots = 2L * sms;
+    // Model fitted to measurements on B200 (profiles/r01_kernel_bench.txt, tools/tp8_shapes.py; within ~10 % for 32..256
+    // (sequence, kv-head) units): a CTA has ~3 us of fixed time, streams its 32 KB tiles at min(60 GB/s -- what its 96 KB ring
+    // sustains --, HBM / resident CTAs), CTAs beyond 2*SMs are back-filled (fractional waves), a split adds ~3 us of merge.
+    const double slots = 2.0 * sms, hbm = 6.2e12, r_cta = 60e9, fixed = 3e-6, merge = 3e-6, tile_bytes = 32768.0;
     for (int c = 1; c <= max_tiles; ++c) {
         const int ns = (max_tiles + c - 1) / c;
         if (ns > kAttnMaxSplit) continue;
-        const long ctas = (long)units * ns;
-        const long waves = (ctas + slots - 1) / slots;
-        const double cost = (double)waves * (c + 2.5);
-        if (cost < best - 1e-9 || (std::fabs(cost - best) <= 1e-9 && c > best_c)) {
+        const double ctas = (double)units * ns;
+        const double waves = std::max(1.0, ctas / slots);   // beyond one wave CTAs are back-filled, not lock-stepped
+        const double resident = ctas < slots ? ctas : slots;
+        const double rate = std::min(r_cta, hbm / resident);
+        const double cost = waves * (fixed + c * tile_bytes / rate) + (ns > 1 ? merge : 0.0);
+        if (cost < best * (1.0 - 1e-6) || (std::fabs(cost - best) <= best * 1e-6 && c > best_c)) {
             best = cost;
             best_c = c;
         }
