@@ -47,6 +47,12 @@ int b200_set_pdl(int enable);
 /* Number of kernels this library has launched since load (all threads); used by bench.py for "gpu_launches". */
 uint64_t b200_launch_count(void);
 
+/* Launch shapes the library will choose (host-only, no CUDA work): how many sequence splits / 64-token tiles per CTA the
+ * attention takes for `units` = batch*kv_heads and a given max_seq_len, and the split-K of a GEMM. For capacity planning
+ * (workspaces) and for tests of the heuristics. */
+int b200_plan_attn_split(int units, int max_seq_len, int* nsplit, int* tiles_per_split);
+int b200_plan_gemm_split(int K, int N, int* nsplit, int* k_blocks_per_split);
+
 /* ------------------------------------------------------------------------------------------------ indexing */
 
 /* Replaces invokeConvertOffsetToBlockArrayData

@@ -272,6 +272,19 @@ int b200_device_check(int device) {
     return B200_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ launch-shape introspection
+int b200_plan_attn_split(int units, int max_seq_len, int* nsplit, int* tiles_per_split) {
+    ARG_CHECK(units > 0 && max_seq_len > 0 && nsplit && tiles_per_split, "plan_attn_split: bad argument");
+    attn_split(units, (max_seq_len + kAttnTile - 1) / kAttnTile, nsplit, tiles_per_split);
+    return B200_OK;
+}
+
+int b200_plan_gemm_split(int K, int N, int* nsplit, int* k_blocks_per_split) {
+    ARG_CHECK(K > 0 && K % kGemmBK == 0 && N > 0 && nsplit && k_blocks_per_split, "plan_gemm_split: bad argument");
+    gemm_split((N + kGemmTileN - 1) / kGemmTileN, K / kGemmBK, env_int("B200_GEMM_CLUSTER", 1) ? 8 : 16, nsplit, k_blocks_per_split);
+    return B200_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ indexing
 int b200_convert_block_table(int32_t* page_list, const int32_t* block_ids, int batch, int max_blocks, void* stream) {
     ARG_CHECK(page_list && block_ids, "convert_block_table: null pointer");

@@ -48,3 +48,31 @@ def test_sass_uses_the_blackwell_paths():
     sass = subprocess.run([cuobjdump, "-sass", build.build()], capture_output=True, text=True).stdout
     for mnem in ("UTCHMMA", "STTM", "LDTM", "UTMALDG", "UBLKCP"):
         assert mnem in sass, mnem
+
+
+def test_launch_shape_heuristics_on_the_baseline_shapes():
+    """Host-only: the split choices that the B200 measurements (profiles/) showed to be best."""
+    import ctypes
+    lib = _lib.load()
+
+    def attn(units, seq):
+        ns, c = ctypes.c_int(), ctypes.c_int()
+        assert lib.b200_plan_attn_split(units, seq, ctypes.byref(ns), ctypes.byref(c)) == 0
+        return ns.value, c.value
+
+    def gemm(K, N):
+        ns, kb = ctypes.c_int(), ctypes.c_int()
+        assert lib.b200_plan_gemm_split(K, N, ctypes.byref(ns), ctypes.byref(kb)) == 0
+        return ns.value, kb.value
+    assert attn(32 * 8, 2048) == (1, 32)          # Llama-3-8B B32 ctx2048: one CTA per (sequence, kv head), 94 % of HBM peak
+    assert attn(32 * 4, 2048) == (1, 32)          # TP2 per-rank shape
+    assert attn(32 * 1, 2048) == (4, 8)           # TP8 per-rank shape
+    ns, c = attn(8, 4096)                          # batch 1: split the sequence to fill the GPU
+    assert ns > 1 and ns * c >= 64
+    assert gemm(4096, 28672) == (1, 32)           # w13: 224 tiles, no split
+    ns, kb = gemm(4096, 4096)                     # o-proj: 32 tiles -> cluster of 8 along k
+    assert ns == 8 and kb == 4
+    ns, kb = gemm(4096, 6144)                     # qkv: 48 tiles -> cluster of 4
+    assert ns == 4 and kb == 8
+    assert gemm(4096, 128256)[0] == 1             # lm_head: > one wave of tiles, never split
+    assert lib.b200_plan_gemm_split(100, 64, None, None) == -1

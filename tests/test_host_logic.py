@@ -77,3 +77,18 @@ def test_attn_op_support_gate():
     C.size_per_head = 64
     I.is_prefill = False
     assert attention.B200DecodeAttnOp(C()).support(I()) is False          # head_dim 128 only
+
+
+def test_bench_reference_arm_runs_on_cpu_and_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times beside ours) needs no GPU and prints one JSON line."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--model", "tiny", "--batch", "2",
+                          "--ctx", "64"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "tokens/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
