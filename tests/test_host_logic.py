@@ -92,3 +92,37 @@ def test_bench_reference_arm_runs_on_cpu_and_prints_the_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "tokens/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_algorithmic_bytes_match_baseline_md():
+    """SURVEY 8(d) / BASELINE.md section 3: the bytes the roofline fraction is computed from."""
+    import dataclasses
+    from rtp_llm_b200.decode_step import LLAMA3_8B, weight_bytes
+    cfg = LLAMA3_8B
+    H, qkv_n, I = cfg.hidden, (cfg.head_num + 2 * cfg.kv_head_num) * cfg.head_dim, cfg.inter
+    per_layer = lambda c: (weight_bytes(c, H, qkv_n) + weight_bytes(c, cfg.head_num * cfg.head_dim, H)
+                           + weight_bytes(c, H, 2 * I) + weight_bytes(c, I, H))
+    assert H * qkv_n + cfg.head_num * cfg.head_dim * H + H * 2 * I + I * H == 218_103_808          # E per layer
+    assert abs(per_layer(dataclasses.replace(cfg, quant="int4")) * cfg.layers - 3.708e9) < 5e6
+    assert abs(per_layer(dataclasses.replace(cfg, quant="f16")) * cfg.layers - 13.959e9) < 5e6
+    assert abs(per_layer(dataclasses.replace(cfg, quant="int8")) * cfg.layers - 6.982e9) < 5e6
+    kv = 2 * 32 * 2048 * cfg.kv_head_num * cfg.head_dim * 2 * cfg.layers
+    assert abs(kv - 8.590e9) < 5e6 and abs(2 * H * cfg.vocab - 1.051e9) < 1e6
+
+
+def test_gate_up_interleave_order():
+    """ops.gate_up_order: every 128-column tile = [64 gate columns j.. | the 64 up columns j..] (fused SiLU*mul layout)."""
+    from rtp_llm_b200 import ops
+    inter = 192
+    order = ops.gate_up_order(inter)
+    assert sorted(order.tolist()) == list(range(2 * inter))
+    for t in range(inter // 64):
+        tile = order[t * 128:(t + 1) * 128]
+        assert tile[:64].tolist() == list(range(t * 64, t * 64 + 64))
+        assert tile[64:].tolist() == list(range(inter + t * 64, inter + t * 64 + 64))
+    w = torch.arange(2 * inter).repeat(3, 1)
+    assert torch.equal(ops.interleave_gate_up(w, inter)[0], order)
+    # packed int4: bytes hold column pairs, so the byte order is the pair order
+    packed = (torch.arange(inter) * 1).to(torch.uint8).repeat(2, 1)          # byte j <-> columns (2j, 2j+1)
+    got = ops.interleave_gate_up(packed, inter, packed_int4=True)[0].long()
+    assert got.tolist() == (order.reshape(-1, 2)[:, 0] // 2).tolist()
