@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--ctx", type=int, default=2048)
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("B200_PDL", "1")))  # programmatic dependent launch (bit-identical results)
+    ap.add_argument("--program", type=int, default=int(os.environ.get("B200_PROGRAM", "1")))  # record the step into a decode program (persistent kernel between attention calls)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--comm", default=os.environ.get("B200_COMM", "peer"), choices=["peer", "nccl"])
     return ap.parse_args()
@@ -197,6 +198,9 @@ def main():
         comm = make_comm(dev, kind=args.comm)
 
     model = DecodeStep(cfg, args.batch, args.ctx, dev, tp_rank=rank, tp_size=tp, comm=comm, pdl=bool(args.pdl))
+    use_program = bool(args.program) and (tp == 1 or args.comm == "peer")
+    if use_program:
+        model.build_program()
     launches_per_step = model.launches_per_step()
     model.capture()
 
@@ -276,7 +280,7 @@ def main():
             "config": {"workload": workload, "global_batch": args.batch, "seq_len": args.ctx,
                        "parallelism": f"tp{tp}", "tp_allreduce": (args.comm if tp > 1 else None), "page_size": cfg.tokens_per_block, "cuda_graph": True,
                        "l2": "inputs larger than L2 (each step streams %.2f GB of weights + KV per GPU)" % (ab["total"] / 1e9),
-                       "pdl": bool(args.pdl)},
+                       "pdl": bool(args.pdl), "decode_program": use_program},
             "e2e": {"value": args.batch / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": model.h2d_bytes(),
                     "d2h_bytes_per_step": model.d2h_bytes(), "ms_per_step": ms_e2e},
             "gpu_launches": launches_per_step * args.steps,

@@ -106,7 +106,8 @@ int b200_pack_w4(const uint8_t* q_packed, const void* scales, const void* zeros_
                  void* blob, void* stream);
 int b200_pack_w8(const int8_t* q, int K, int N, void* blob, void* stream);
 
-/* Scratch for split-K partials + semaphores; zero-fill once after allocation. */
+/* Scratch for split-K / stream-K partials + semaphores (+ the grid-barrier words of a stand-alone call); zero-fill once
+ * after allocation. Always required for INT8 / INT4 weights (at least 16 KiB). */
 size_t b200_wo_gemm_workspace_bytes(int max_batch, int N, int K);
 
 /* Y[B][N] = X[B][K] . W' (+ bias).  The compute behind LinearBase.forward
@@ -154,13 +155,27 @@ int b200_peer_open(const void* ipc_handle, void** ptr);
 int b200_peer_allreduce(const void* in, void* out, size_t bytes, int is_bf16, void* const* regions, size_t max_message_bytes,
                         int call_parity, int rank, int world, void* stream);
 
-/* ------------------------------------------------------------------------------------------------ GPU-side checkers */
-/* Deliberately naive CUDA-core kernels over the UN-permuted reference tensors; used by tests only. */
-int b200_ref_paged_decode_attn(const void* q, int is_bf16, void* out, int head_num, int kv_head_num, int head_dim,
-                               int batch, int max_blocks_per_seq, int page_size, const void* kv_pool,
-                               const int32_t* page_list, const int32_t* sequence_lengths, float q_scale, void* stream);
-int b200_ref_dequant_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const void* w, const void* scales,
-                          const void* zeros_x_scales, int group, const void* bias, void* y, void* stream);
+/* ------------------------------------------------------------------------------------------------ decode programs */
+
+/* A decode program is a recorded sequence of the op calls above, replayed with far fewer launches -- the B200 counterpart
+ * of the reference's CUDA-graph capture of the decode step (rtp_llm/cpp/cuda_graph/cuda_graph_runner.cc: capture once per
+ * batch size, replay every step).  Between b200_program_begin and b200_program_end every op call of the CALLING THREAD is
+ * appended to the program instead of being launched (arguments are checked and launch shapes planned at record time;
+ * pointers and sizes are frozen, exactly as under stream capture).  Consecutive weight-only GEMMs, norms, rope+append,
+ * embedding and block-table ops are fused into ONE persistent kernel (2 CTAs per SM, grid-wide barriers between ops,
+ * stream-K GEMMs, weights prefetched across op boundaries -- csrc/decode_program.cuh); attention, FP16 GEMMs, argmax and
+ * all-reduce calls are replayed as their own launches in order.  b200_program_launch never allocates or synchronises and
+ * may itself be captured into a CUDA graph.  b200_program_end allocates the device-side op table (once).
+ * Results are identical to issuing the same calls one by one (same kernels' arithmetic; tests compare bit for bit). */
+typedef struct b200_program b200_program;
+int b200_program_create(b200_program** out);
+int b200_program_begin(b200_program* p);
+int b200_program_end(b200_program* p);
+int b200_program_launch(b200_program* p, void* stream);
+int b200_program_num_ops(const b200_program* p);      /* ops fused into persistent-kernel segments */
+int b200_program_num_launches(const b200_program* p); /* kernel launches per b200_program_launch */
+int b200_program_set_trace(b200_program* p, void* device_buffer); /* developer: per-op, per-CTA globaltimer stamps */
+int b200_program_destroy(b200_program* p);
 
 #ifdef __cplusplus
 }

@@ -381,28 +381,29 @@ void oracle_dequant_gemm_fast(const h16* x, int is_bf16, int B, int K, int N, in
 /* Glue ops of the decode step          */
 /* ------------------------------------------------------------------ */
 
-/* RMSNorm with optional fused residual add:
- * rtp_llm/models_py/bindings/common/kernels/layernorm_kernels.cu (rmsnorm / fused_add_rmsnorm as bound in
- * cuda/RegisterBaseBindings.hpp:45-160): residual += x (stored back, rounded to elem); y = residual * rsqrt(mean(r^2)+eps) * gamma */
+/* RMSNorm with optional fused residual add, as bound in rtp_llm/models_py/bindings/cuda/RegisterBaseBindings.hpp:45-60
+ * (rmsnorm / fused_add_rmsnorm -> 3rdparty/flashinfer/flashinfer.h:30, flashinfer norm.cuh FusedAddRMSNormKernel):
+ * x = float(in) + float(residual) is kept UNROUNDED for the sum of squares and for the output; only the value stored back
+ * to `residual` is rounded to the element type.  y = x * rsqrt(mean(x^2) + eps) * gamma. */
 void oracle_add_rmsnorm(const h16* x, h16* residual, const h16* gamma, h16* y, int is_bf16, int rows, int hidden,
                         float eps, int has_residual) {
+    float* row = (float*)malloc((size_t)hidden * sizeof(float));
     for (int r = 0; r < rows; ++r) {
         double ss = 0.0;
         for (int c = 0; c < hidden; ++c) {
             float v = elem_to_float(x[(size_t)r * hidden + c], is_bf16);
             if (has_residual) {
-                v = round_elem(v + elem_to_float(residual[(size_t)r * hidden + c], is_bf16), is_bf16);
+                v = v + elem_to_float(residual[(size_t)r * hidden + c], is_bf16);
                 residual[(size_t)r * hidden + c] = float_to_elem(v, is_bf16);
             }
+            row[c] = v;
             ss += (double)v * v;
         }
         float inv = 1.0f / sqrtf((float)(ss / hidden) + eps);
-        for (int c = 0; c < hidden; ++c) {
-            float v = has_residual ? elem_to_float(residual[(size_t)r * hidden + c], is_bf16)
-                                   : elem_to_float(x[(size_t)r * hidden + c], is_bf16);
-            y[(size_t)r * hidden + c] = float_to_elem(v * inv * elem_to_float(gamma[c], is_bf16), is_bf16);
-        }
+        for (int c = 0; c < hidden; ++c)
+            y[(size_t)r * hidden + c] = float_to_elem(row[c] * inv * elem_to_float(gamma[c], is_bf16), is_bf16);
     }
+    free(row);
 }
 
 /* SiLU(gate) * up on a [rows][2*inter] buffer (gate first), activation_kernels.cu silu_and_mul semantics. */

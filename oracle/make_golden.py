@@ -10,6 +10,8 @@ What is imported from the reference (unmodified, loaded from /root/reference by 
                                        symmetric_quantize_last_axis_of_batched_matrix, unpack/reverse/pack helpers,
                                        CudaImpl.preprocess_weights_for_mixed_gemm (FT layout, kept as a fixture only)
   * rtp_llm/models_py/modules/factory/attention/cuda_impl/test/atten_test_util.py   attention_prefill_ref
+  * .../cuda_impl/test/test_flashinfer_prefill/test_mha_rotary_emb.py   create_cos_sin_cache, apply_rope_reference
+                                       (the two functions are extracted by name and executed unmodified)
 The modules' unrelated imports (rtp_llm.ops, config, ...) are stubbed because the compiled ops library cannot be
 built here (bazel-only).  Expected indexing values follow the reference tests' own
 expected-value builders (test_py_flashinfer_mha_decode.py:66-89, trtllm_gen_test.py:305-314), restated here.
@@ -165,6 +167,45 @@ def gen_attention(att):
         print(name, "expect", expect.shape, float(np.abs(expect).max()))
 
 
+def _ref_functions(path, names):
+    """Extract top-level functions of a reference file BY NAME and execute them unmodified (the file's own imports need
+    CUDA / the compiled ops library; the functions themselves are pure torch)."""
+    import ast
+    from typing import Tuple
+    src = open(path).read()
+    tree = ast.parse(src)
+    ns = {"torch": torch, "Tuple": Tuple, "math": math}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return [ns[n] for n in names]
+
+
+def gen_rope():
+    """RoPE (RopeStyle::Base, NeoX / non-interleaved pairing) goldens from the reference's pure-torch implementation:
+    create_cos_sin_cache + apply_rope_reference, test_flashinfer_prefill/test_mha_rotary_emb.py:47-81,121-165 -- the oracle
+    its own fused-rope kernel tests compare against (rtol = atol = 1e-2, :506-507). Decode: one token per sequence at
+    position sequence_lengths[b]; computed in fp32 and rounded to fp16 exactly as the reference test does (:272-276)."""
+    path = f"{REF}/rtp_llm/models_py/modules/factory/attention/cuda_impl/test/test_flashinfer_prefill/test_mha_rotary_emb.py"
+    create_cos_sin_cache, apply_rope_reference = _ref_functions(path, ["create_cos_sin_cache", "apply_rope_reference"])
+    g = torch.Generator().manual_seed(7)
+    for name, B, Hq, Hkv, D, base, max_pos in (("rope_base10000", 5, 8, 2, 128, 10000.0, 4096),
+                                               ("rope_base500000", 4, 4, 4, 128, 500000.0, 8192),
+                                               ("rope_d64", 3, 4, 1, 64, 10000.0, 2048)):
+        qkv = torch.randn(B, (Hq + 2 * Hkv) * D, generator=g).half()
+        positions = torch.randint(0, max_pos, (B,), generator=g)
+        positions[0] = 0
+        positions[-1] = max_pos - 1
+        cache = create_cos_sin_cache(D, max_pos, base, device="cpu")
+        q = qkv[:, : Hq * D].reshape(B, Hq, D)
+        k = qkv[:, Hq * D:(Hq + Hkv) * D].reshape(B, Hkv, D)
+        q_ref, k_ref = apply_rope_reference(q.float(), k.float(), cache.float(), positions)
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), qkv=qkv.numpy(), positions=positions.numpy().astype(np.int32),
+                            q_rope=q_ref.half().numpy(), k_rope=k_ref.half().numpy(), head_num=Hq, kv_head_num=Hkv,
+                            head_dim=D, rope_base=np.float32(base))
+        print(name, tuple(q_ref.shape), tuple(k_ref.shape))
+
+
 def gen_indexing():
     """Expected values built the way the reference tests build them."""
     rng = np.random.default_rng(42)
@@ -200,4 +241,5 @@ if __name__ == "__main__":
     dev, att = load_reference()
     gen_quant(dev)
     gen_attention(att)
+    gen_rope()
     gen_indexing()

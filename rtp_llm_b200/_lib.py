@@ -38,9 +38,14 @@ SIGNATURES = {
     "b200_peer_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
     "b200_peer_open": (c_int, [c_void_p, c_void_p]),
     "b200_peer_allreduce": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
-    "b200_ref_paged_decode_attn": (c_int, [c_void_p, c_int, c_void_p] + [c_int] * 6 + [c_void_p] * 3 + [c_float, c_void_p]),
-    "b200_ref_dequant_gemm": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_int] + [c_void_p] * 3 + [c_int, c_void_p,
-                                      c_void_p, c_void_p]),
+    "b200_program_create": (c_int, [c_void_p]),
+    "b200_program_begin": (c_int, [c_void_p]),
+    "b200_program_end": (c_int, [c_void_p]),
+    "b200_program_launch": (c_int, [c_void_p, c_void_p]),
+    "b200_program_num_ops": (c_int, [c_void_p]),
+    "b200_program_num_launches": (c_int, [c_void_p]),
+    "b200_program_set_trace": (c_int, [c_void_p, c_void_p]),
+    "b200_program_destroy": (c_int, [c_void_p]),
 }
 
 _lib = None

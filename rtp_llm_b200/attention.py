@@ -74,7 +74,9 @@ class B200DecodeAttnOp:
             raise B200Error(f"kv blocks batch size expected [{B}] but got [{block_ids.shape[0]}]")
         page_list = ops.convert_block_table(block_ids)
         max_seq_len = int(getattr(self.cfg, "max_seq_len", 0)) or int(block_ids.shape[1]) * _tokens_per_block(self.cfg)
-        max_seq_len = min(max_seq_len, int(block_ids.shape[1]) * _tokens_per_block(self.cfg))
+        # sequence_lengths may equal max_seq_len (tokens already cached): the kernel covers positions 0..sequence_lengths
+        # inclusive, so the bound is max_seq_len + 1 exactly as XQAAttnOp.cc:147-149 passes it, capped by the page table
+        max_seq_len = min(max_seq_len + 1, int(block_ids.shape[1]) * _tokens_per_block(self.cfg))
         ws = ops.attn_workspace(B, self.cfg.head_num, self.cfg.kv_head_num, max_seq_len, block_ids.device)
         return B200AttnParams(page_list, attn_inputs.sequence_lengths, B, max_seq_len, ws)
 

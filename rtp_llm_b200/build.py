@@ -5,32 +5,65 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
+OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb200_decode.so")
-SOURCES = ["c_api.cu"]
-HEADERS = ["ptx.cuh", "paged_decode_attn.cuh", "wo_gemm.cuh", "aux_kernels.cuh", "../../include/b200_decode_ops.h"]
-NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-shared",
+# translation units compile in parallel (the persistent-kernel instantiations dominate the build time)
+SOURCES = ["c_api.cu", "gemm_cluster.cu", "segment_f16.cu", "segment_bf16.cu"]
+NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
               "-Xcompiler", "-fPIC", "-DB200_BUILD"]
-if os.environ.get("B200_DEV"):           # developer build: clock64 timeline + ablation switches in the GEMM (tools/gemm_trace.py)
+if os.environ.get("B200_DEV"):           # developer build: clock64 timeline + ablation switches in the cluster GEMM (tools/gemm_trace.py)
     NVCC_FLAGS.append("-DB200_GEMM_DEV")
+TESTREF_SRC = os.path.join(ROOT, "tests", "native", "test_ref.cu")
+TESTREF_LIB = os.path.join(ROOT, "tests", "native", "libb200_testref.so")
+
+
+def _deps():
+    """Every header of csrc/ plus the public header: an edited kernel can never run against a stale library."""
+    hdr = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    return hdr + [os.path.join(ROOT, "include", "b200_decode_ops.h"), os.path.abspath(__file__)]
+
+
+def _newer(target: str, deps) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
 
 
 def _stale() -> bool:
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return _newer(LIB, _deps() + [os.path.join(CSRC, s) for s in SOURCES])
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
-    subprocess.check_call(cmd)
+    os.makedirs(OBJDIR, exist_ok=True)
+    hdrs = _deps()
+
+    def compile_one(src):
+        obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        path = os.path.join(CSRC, src)
+        if force or _newer(obj, hdrs + [path]):
+            subprocess.check_call([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj])
+        return obj
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"])
     return LIB
+
+
+def build_testref(force: bool = False) -> str:
+    """tests/native/libb200_testref.so: naive CUDA-core checkers used by the GPU tests only (not part of the product)."""
+    if not force and not _newer(TESTREF_LIB, [TESTREF_SRC, os.path.join(CSRC, "ptx.cuh")]):
+        return TESTREF_LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    subprocess.check_call([nvcc, "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-shared", "-Xcompiler", "-fPIC",
+                           "-o", TESTREF_LIB, TESTREF_SRC, "-lcudart"])
+    return TESTREF_LIB
 
 
 PYBIND_SO = os.path.join(HERE, "b200_compute_ops.so")

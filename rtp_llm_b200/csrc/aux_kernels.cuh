@@ -1,6 +1,5 @@
 // Small HBM-bound kernels either side of the two hot kernels: page-table indexing, the glue ops of a decode layer
-// (SURVEY.md section 8f rows 1-3), greedy sampling, and deliberately naive CUDA-core reference kernels used only by the
-// GPU parity tests at sizes the CPU oracle cannot reach.
+//  and greedy sampling.
 #pragma once
 #include "ptx.cuh"
 
@@ -9,7 +8,7 @@ namespace b200 {
 // ---------------------------------------------------------------------------------------------- indexing
 // block table [B][M] -> page list [B][2][M] (K = 2*id, V = 2*id+1); bit-exact restatement of the behaviour of
 // /root/reference/rtp_llm/models_py/bindings/common/kernels/kv_cache_kernels.cu:49-63.
-__global__ void convert_block_table_kernel(int32_t* __restrict__ page_list, const int32_t* __restrict__ block_ids,
+static __global__ void convert_block_table_kernel(int32_t* __restrict__ page_list, const int32_t* __restrict__ block_ids,
                                            int batch, int max_blocks) {
     const int total = batch * max_blocks;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -22,7 +21,7 @@ __global__ void convert_block_table_kernel(int32_t* __restrict__ page_list, cons
 
 // decode-mode flashinfer plan metadata (mha_paged_attn_plan.cu:28-97, decode branch + prefill branch).
 // One CTA; a warp-shuffle scan replaces the reference's thread-0 serial scan.
-__global__ void paged_attn_plan_kernel(const int32_t* __restrict__ input_lengths,
+static __global__ void paged_attn_plan_kernel(const int32_t* __restrict__ input_lengths,
                                        const int32_t* __restrict__ sequence_lengths,
                                        const int32_t* __restrict__ prefix_lengths,
                                        const int32_t* __restrict__ block_ids, int batch, int max_blocks,
@@ -105,8 +104,9 @@ __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t v) {
     return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
 }
 
-// y = rmsnorm(x (+ residual)) * gamma; residual (if given) is updated in place with x + residual (rounded to T).
-// One CTA per row, 16-byte vector loads, hidden % 8 == 0.  (fused_add_rmsnorm / rmsnorm of RegisterBaseBindings.hpp:45-160)
+// y = rmsnorm(x (+ residual)) * gamma; residual (if given) is updated in place with x + residual (rounded to T), while the
+// UNROUNDED fp32 sum feeds both the variance and the output -- the numerics of the op the reference binds
+// (RegisterBaseBindings.hpp:45-60 -> flashinfer FusedAddRMSNormKernel). One CTA per row, 16-byte vector loads, hidden % 8 == 0.
 template <typename T>
 __global__ void add_rmsnorm_kernel(const T* __restrict__ x, T* __restrict__ residual, const T* __restrict__ gamma,
                                    T* __restrict__ y, int hidden, float eps) {
@@ -120,24 +120,22 @@ __global__ void add_rmsnorm_kernel(const T* __restrict__ x, T* __restrict__ resi
     float ss = 0.f;
     for (int i = threadIdx.x; i < hidden / 8; i += blockDim.x) {
         uint4 a = xv[i];
-        uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+        uint32_t rw[4] = {0u, 0u, 0u, 0u}, ow[4];
         if (rv) {
             uint4 r = rv[i];
-            uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float2 fa = unpack2<T>(aw[j]), fr = unpack2<T>(rw[j]);
-                aw[j] = pack2<T>(fa.x + fr.x, fa.y + fr.y);
-            }
-            rv[i] = make_uint4(aw[0], aw[1], aw[2], aw[3]);
+            rw[0] = r.x; rw[1] = r.y; rw[2] = r.z; rw[3] = r.w;
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float2 f = unpack2<T>(aw[j]);
-            s_row[i * 8 + j * 2] = f.x;
-            s_row[i * 8 + j * 2 + 1] = f.y;
-            ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss));
+            const float2 fa = unpack2<T>(aw[j]), fr = unpack2<T>(rw[j]);
+            const float x0 = fa.x + fr.x, x1 = fa.y + fr.y;
+            s_row[i * 8 + j * 2] = x0;
+            s_row[i * 8 + j * 2 + 1] = x1;
+            ss = fmaf(x0, x0, fmaf(x1, x1, ss));
+            ow[j] = pack2<T>(x0, x1);
         }
+        if (rv) rv[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -284,68 +282,4 @@ __global__ void argmax_kernel(const T* __restrict__ logits, int vocab, int32_t* 
         if (threadIdx.x == 0) out[blockIdx.x] = bi;
     }
 }
-// ---------------------------------------------------------------------------------------------- naive references
-// (GPU-side checkers for the parity tests; CUDA cores only, no tiling, obviously-correct indexing)
-template <typename T>
-__global__ void ref_paged_decode_attn_kernel(const T* __restrict__ q, T* __restrict__ out,
-                                             const T* __restrict__ kv_pool, const int32_t* __restrict__ page_list,
-                                             const int32_t* __restrict__ seq_lens, int Hq, int Hkv, int D, int M,
-                                             int tokens_per_block, float scale) {
-    // one warp per (b, h); online softmax in fp32; lanes split the head dim
-    const int b = blockIdx.x, h = blockIdx.y, lane = threadIdx.x;
-    const int kvh = h / (Hq / Hkv), len = seq_lens[b] + 1;
-    const size_t page_elems = (size_t)Hkv * tokens_per_block * D;
-    const int per = D / 32;  // <= 8
-    float qf[8], acc[8];
-    for (int j = 0; j < per; ++j) {
-        qf[j] = to_f32<T>(q[((size_t)b * Hq + h) * D + lane * per + j]);
-        acc[j] = 0.f;
-    }
-    float m = -INFINITY, l = 0.f;
-    for (int t = 0; t < len; ++t) {
-        const size_t in_page = ((size_t)kvh * tokens_per_block + t % tokens_per_block) * D;
-        const T* kr = kv_pool + (size_t)page_list[((size_t)b * 2 + 0) * M + t / tokens_per_block] * page_elems + in_page;
-        const T* vr = kv_pool + (size_t)page_list[((size_t)b * 2 + 1) * M + t / tokens_per_block] * page_elems + in_page;
-        float s = 0.f;
-        for (int j = 0; j < per; ++j) s += qf[j] * to_f32<T>(kr[lane * per + j]);
-#pragma unroll
-        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        s *= scale;
-        const float mn = fmaxf(m, s), a = expf(m - mn), pw = expf(s - mn);
-        l = l * a + pw;
-        for (int j = 0; j < per; ++j) acc[j] = acc[j] * a + pw * to_f32<T>(vr[lane * per + j]);
-        m = mn;
-    }
-    for (int j = 0; j < per; ++j) out[((size_t)b * Hq + h) * D + lane * per + j] = from_f32<T>(acc[j] / l);
-}
-
-// Y = X . W' from the UN-permuted reference tensors (fmt 0: W[K][N] T; 1: q int8 [K][N] + scale[N]; 2: q_packed [K][N/2]
-// + scales/zs [K/g][N]); one thread per output, fp32 accumulate, W' rounded to T exactly like the oracle.
-template <typename T>
-__global__ void ref_dequant_gemm_kernel(const T* __restrict__ x, int B, int K, int N, int fmt,
-                                        const void* __restrict__ w, const T* __restrict__ scales,
-                                        const T* __restrict__ zs, int group, const T* __restrict__ bias,
-                                        T* __restrict__ y) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-    if (n >= N) return;
-    float acc = 0.f;
-    for (int k = 0; k < K; ++k) {
-        float wv;
-        if (fmt == 0) {
-            wv = to_f32<T>(reinterpret_cast<const T*>(w)[(size_t)k * N + n]);
-        } else if (fmt == 1) {
-            wv = to_f32<T>(from_f32<T>((float)reinterpret_cast<const int8_t*>(w)[(size_t)k * N + n] * to_f32<T>(scales[n])));
-        } else {
-            const uint8_t byte = reinterpret_cast<const uint8_t*>(w)[(size_t)k * (N / 2) + n / 2];
-            int nib = (n & 1) ? (byte >> 4) : (byte & 0xF);
-            nib = (nib & 8) ? nib - 16 : nib;
-            wv = to_f32<T>(from_f32<T>(fmaf((float)nib, to_f32<T>(scales[(size_t)(k / group) * N + n]),
-                                           to_f32<T>(zs[(size_t)(k / group) * N + n]))));
-        }
-        acc = fmaf(to_f32<T>(x[(size_t)b * K + k]), wv, acc);
-    }
-    if (bias) acc += to_f32<T>(bias[n]);
-    y[(size_t)b * N + n] = from_f32<T>(acc);
-}
-
 }  // namespace b200

@@ -1,5 +1,6 @@
 // C-ABI entry points of libb200_decode.so (declared in include/b200_decode_ops.h).
-// Host side only: argument checks, tensor-map encoding, launch-shape heuristics, launches. No torch, no allocation.
+// Host side only: argument checks, tensor-map encoding, launch-shape heuristics, launches, and the recorder that turns a
+// sequence of op calls into a decode program (b200_program_*). No torch, no allocation on the op path.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -10,21 +11,25 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
+#include <vector>
 
-#include "../../include/b200_decode_ops.h"
 #include "aux_kernels.cuh"
+#include "decode_program.cuh"
+#include "internal.h"
 #include "paged_decode_attn.cuh"
 #include "peer_allreduce.cuh"
 #include "wo_gemm.cuh"
 
 using namespace b200;
+using namespace b200_host;
 
-namespace {
+namespace b200_host {
 
 thread_local std::string g_err;
-std::atomic<uint64_t> g_launches{0};
+static std::atomic<uint64_t> g_launches{0};
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -35,15 +40,6 @@ int fail(int code, const char* fmt, ...) {
     g_err = buf;
     return code;
 }
-#define ARG_CHECK(cond, ...)                                \
-    do {                                                    \
-        if (!(cond)) return fail(B200_EINVAL, __VA_ARGS__); \
-    } while (0)
-#define CUDA_CHECK(expr)                                                                               \
-    do {                                                                                               \
-        cudaError_t _e = (expr);                                                                       \
-        if (_e != cudaSuccess) return fail(B200_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
-    } while (0)
 
 int launched(const char* what) {
     cudaError_t e = cudaPeekAtLastError();
@@ -54,6 +50,42 @@ int launched(const char* what) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return B200_OK;
 }
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+int num_sms() {
+    static int sms[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16) return 148;
+    if (!sms[dev]) {
+        cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (sms[dev] <= 0) sms[dev] = 148;
+    }
+    return sms[dev];
+}
+
+int seg_dispatch_f16(int bpad, int qfmt, const ProgOp* op0, const ProgOp* d_ops, int nops, unsigned* gbar, int grid, bool pdl,
+                     unsigned long long* trace, cudaStream_t st, int* grid_out);
+int seg_dispatch_bf16(int bpad, int qfmt, const ProgOp* op0, const ProgOp* d_ops, int nops, unsigned* gbar, int grid, bool pdl,
+                      unsigned long long* trace, cudaStream_t st, int* grid_out);
+
+int segment_grid(bool bf16, int bpad, int qfmt, int* grid_out) {
+    return bf16 ? seg_dispatch_bf16(bpad, qfmt, nullptr, nullptr, 0, nullptr, 0, false, nullptr, nullptr, grid_out)
+                : seg_dispatch_f16(bpad, qfmt, nullptr, nullptr, 0, nullptr, 0, false, nullptr, nullptr, grid_out);
+}
+int launch_segment(bool bf16, int bpad, int qfmt, const ProgOp* op0, const ProgOp* d_ops, int nops, unsigned* gbar, int grid,
+                   bool pdl, unsigned long long* trace, cudaStream_t st) {
+    return bf16 ? seg_dispatch_bf16(bpad, qfmt, op0, d_ops, nops, gbar, grid, pdl, trace, st, nullptr)
+                : seg_dispatch_f16(bpad, qfmt, op0, d_ops, nops, gbar, grid, pdl, trace, st, nullptr);
+}
+
+}  // namespace b200_host
+
+namespace {
 
 std::atomic<int> g_pdl{0};
 
@@ -73,22 +105,6 @@ cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
-}
-
-int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
-
-int num_sms() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
 }
 
 // ---- cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
@@ -159,9 +175,8 @@ void attn_split(int units, int max_tiles, int* nsplit, int* tiles_per_split) {
 
 // ---- GEMM launch shape
 int gemm_bpad(int B) { return B <= 16 ? 16 : (B <= 32 ? 32 : (B <= 64 ? 64 : 128)); }
+// one-kernel-per-GEMM path (gemm_cluster.cu): split-K so that one wave of 2*SMs CTAs is filled
 void gemm_split(int n_tiles, int k_blocks, int max_split, int* nsplit, int* kb_per_split) {
-    // Measured (profiles/r01_gemm_trace.txt): a CTA spends ~0.4 us per 128-deep k-block plus ~1.5-2 us of fixed time, two
-    // CTAs are resident per SM, and the split-K merge costs ~1 us. So: fill one wave of 2*SMs slots, then shorten chains.
     const int forced = env_int("B200_GEMM_SPLITK", 0);
     const long slots = 2L * num_sms();
     int best_s = 1;
@@ -188,66 +203,106 @@ void gemm_split(int n_tiles, int k_blocks, int max_split, int* nsplit, int* kb_p
     *kb_per_split = kbp;
     *nsplit = (k_blocks + kbp - 1) / kbp;
 }
-constexpr size_t kGemmSemBytes = 16384;
+constexpr size_t kGemmSemBytes = 16384;      // [n_tiles] tile semaphores ... [last 64 bytes] grid-barrier words of a stand-alone call
 
-template <int FMT, typename T, int BPAD, int VAR>
-int launch_gemm_var(const CUtensorMap& xmap, const CUtensorMap& wmap, const GemmParams& p, int n_tiles, cudaStream_t st) {
-    auto kern = wo_gemm_kernel<FMT, T, BPAD, VAR>;
-    constexpr int smem = gemm_smem_bytes(FMT, BPAD, VAR);
-    static bool configured = false;
-    if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+// stream-K plan of the persistent kernel: the n_tiles*k_blocks work list is cut into runs of `per` k-blocks, one per CTA
+struct SkPlan {
+    int per, used, max_contrib;
+};
+int sk_max_contrib(int n_tiles, int k_blocks, int per) {
+    int mc = 1;
+    for (int t = 0; t < n_tiles; ++t) {
+        const long a = (long)t * k_blocks, b = a + k_blocks - 1;
+        const int c = (int)(b / per - a / per) + 1;
+        if (c > mc) mc = c;
     }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(n_tiles, p.nsplit, 1);
-    cfg.blockDim = dim3(gemm_threads(VAR), 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[2];
-    int na = 0;
-    if (p.use_pdl) {
-        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[na].val.programmaticStreamSerializationAllowed = 1;
-        ++na;
-    }
-    if (p.nsplit > 1 && p.cluster_reduce) {
-        attr[na].id = cudaLaunchAttributeClusterDimension;
-        attr[na].val.clusterDim.x = 1;
-        attr[na].val.clusterDim.y = (unsigned)p.nsplit;
-        attr[na].val.clusterDim.z = 1;
-        ++na;
-    }
-    cfg.attrs = attr;
-    cfg.numAttrs = na;
-    CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, xmap, wmap, p));
-    return launched("wo_gemm_kernel");
+    return mc;
 }
-
-template <int FMT, typename T, int BPAD>
-int launch_gemm(const CUtensorMap& xmap, const CUtensorMap& wmap, const GemmParams& p, int n_tiles, cudaStream_t st) {
-    return launch_gemm_var<FMT, T, BPAD, 0>(xmap, wmap, p, n_tiles, st);
+SkPlan sk_plan(int n_tiles, int k_blocks, int grid, int bpad, size_t ws_partial_bytes) {
+    const long total = (long)n_tiles * k_blocks;
+    int per = (int)((total + grid - 1) / grid);
+    const int min_run = env_int("B200_SK_MIN_RUN", 2);
+    if (per < min_run) per = min_run < k_blocks ? min_run : k_blocks;
+    if (env_int("B200_SK_WHOLE_TILES", 0)) per = (per + k_blocks - 1) / k_blocks * k_blocks;
+    int mc = sk_max_contrib(n_tiles, k_blocks, per);
+    const size_t slot = (size_t)bpad * kGemmTileN * sizeof(float);
+    if (mc > 1 && (size_t)n_tiles * mc * slot > ws_partial_bytes) {
+        per = (per + k_blocks - 1) / k_blocks * k_blocks;   // no room for partials: whole tiles per CTA (always valid)
+        mc = 1;
+    }
+    SkPlan p;
+    p.per = per;
+    p.used = (int)((total + per - 1) / per);
+    p.max_contrib = mc;
+    return p;
+}
+size_t sk_ws_bytes(int n_tiles, int k_blocks, int grid, int bpad) {
+    SkPlan p = sk_plan(n_tiles, k_blocks, grid, bpad, (size_t)-1);
+    return p.max_contrib > 1 ? (size_t)n_tiles * p.max_contrib * bpad * kGemmTileN * sizeof(float) : 0;
 }
 
-template <int FMT, typename T>
-int dispatch_gemm_bpad(int bpad, const CUtensorMap& xmap, const CUtensorMap& wmap, const GemmParams& p, int n_tiles,
-                       cudaStream_t st) {
-    switch (bpad) {
-        case 16: return launch_gemm<FMT, T, 16>(xmap, wmap, p, n_tiles, st);
-        case 32: return launch_gemm<FMT, T, 32>(xmap, wmap, p, n_tiles, st);
-        case 64: return launch_gemm<FMT, T, 64>(xmap, wmap, p, n_tiles, st);
-        default: return launch_gemm<FMT, T, 128>(xmap, wmap, p, n_tiles, st);
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ decode program recorder
+// A program is recorded from ordinary op calls, like a CUDA-graph capture (the reference captures its decode step with
+// cudaStreamBeginCapture in cpp/cuda_graph/cuda_graph_runner.cc): between b200_program_begin and b200_program_end the
+// calling thread's op calls are appended to the program instead of being launched. Consecutive ops the persistent kernel
+// implements (weight-only GEMMs, norms, rope + append, embedding, block-table conversion) become ONE launch; every other
+// op (attention, FP16 GEMMs, argmax, all-reduce) is replayed as its own launch in between.
+struct b200_program {
+    struct Item {
+        bool segment = false;
+        int first = 0, count = 0;          // ops[first, first+count)
+        int bf16 = -1, bpad = -1, qfmt = -1;
+        std::function<int(void*)> fn;      // non-segment: replays the recorded call on a stream
+    };
+    std::vector<ProgOp> ops;
+    std::vector<Item> items;
+    ProgOp* d_ops = nullptr;
+    unsigned* d_bar = nullptr;
+    unsigned long long* trace = nullptr;
+    bool finalized = false;
+    bool fuse = true;
+};
+
+namespace {
+
+thread_local b200_program* g_rec = nullptr;
+
+int rec_segment_op(const ProgOp& op, int bf16, int bpad, int qfmt) {
+    b200_program* P = g_rec;
+    auto compat = [](int a, int b) { return a < 0 || b < 0 || a == b; };
+    if (!P->items.empty()) {
+        b200_program::Item& it = P->items.back();
+        if (it.segment && compat(it.bf16, bf16) && compat(it.bpad, bpad) && compat(it.qfmt, qfmt)) {
+            if (it.bf16 < 0) it.bf16 = bf16;
+            if (it.bpad < 0) it.bpad = bpad;
+            if (it.qfmt < 0) it.qfmt = qfmt;
+            P->ops.push_back(op);
+            ++it.count;
+            return B200_OK;
+        }
     }
+    b200_program::Item it;
+    it.segment = true;
+    it.first = (int)P->ops.size();
+    it.count = 1;
+    it.bf16 = bf16;
+    it.bpad = bpad;
+    it.qfmt = qfmt;
+    P->ops.push_back(op);
+    P->items.push_back(std::move(it));
+    return B200_OK;
 }
-template <typename T>
-int dispatch_gemm_fmt(int fmt, int bpad, const CUtensorMap& xmap, const CUtensorMap& wmap, const GemmParams& p,
-                      int n_tiles, cudaStream_t st) {
-    switch (fmt) {
-        case B200_FMT_F16: return dispatch_gemm_bpad<kFmtF16, T>(bpad, xmap, wmap, p, n_tiles, st);
-        case B200_FMT_INT8: return dispatch_gemm_bpad<kFmtInt8, T>(bpad, xmap, wmap, p, n_tiles, st);
-        default: return dispatch_gemm_bpad<kFmtInt4, T>(bpad, xmap, wmap, p, n_tiles, st);
-    }
+
+int rec_call(std::function<int(void*)> fn) {
+    b200_program::Item it;
+    it.fn = std::move(fn);
+    g_rec->items.push_back(std::move(it));
+    return B200_OK;
 }
+// developer switch B200_PROGRAM_FUSE_MASK: bit (1 << op type) must be set for an op type to be fused (default: all)
+bool recording_fused(int op_type) { return g_rec && g_rec->fuse && ((env_int("B200_PROGRAM_FUSE_MASK", -1) >> op_type) & 1); }
 
 }  // namespace
 
@@ -290,6 +345,16 @@ int b200_convert_block_table(int32_t* page_list, const int32_t* block_ids, int b
     ARG_CHECK(page_list && block_ids, "convert_block_table: null pointer");
     ARG_CHECK(batch >= 0 && max_blocks >= 0, "convert_block_table: negative size");
     if (batch == 0 || max_blocks == 0) return B200_OK;
+    if (recording_fused(kOpBlockTable)) {
+        ProgOp op{};
+        op.type = kOpBlockTable;
+        op.t.page_list = page_list;
+        op.t.block_ids = block_ids;
+        op.t.batch = batch;
+        op.t.max_blocks = max_blocks;
+        return rec_segment_op(op, -1, -1, -1);
+    }
+    if (g_rec) return rec_call([=](void* st) { return b200_convert_block_table(page_list, block_ids, batch, max_blocks, st); });
     const int total = batch * max_blocks;
     const int threads = 256, blocks = (total + threads - 1) / threads;
     convert_block_table_kernel<<<blocks < 1024 ? blocks : 1024, threads, 0, (cudaStream_t)stream>>>(page_list, block_ids,
@@ -308,6 +373,12 @@ int b200_paged_attn_plan(const int32_t* input_lengths, const int32_t* sequence_l
     ARG_CHECK(tokens_per_block > 0, "paged_attn_plan: tokens_per_block must be positive");
     ARG_CHECK(paged_kv_last_page_len && decode_page_indptr && batch_indice && positions, "paged_attn_plan: null output");
     ARG_CHECK(!block_ids || page_indice, "paged_attn_plan: block_ids given but page_indice is null");
+    if (g_rec)
+        return rec_call([=](void* st) {
+            return b200_paged_attn_plan(input_lengths, sequence_lengths, prefix_lengths, block_ids, batch, max_blocks,
+                                        tokens_per_block, paged_kv_last_page_len, decode_page_indptr, page_indice, batch_indice,
+                                        positions, st);
+        });
     const int threads = (batch + 31) / 32 * 32;
     paged_attn_plan_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(input_lengths, sequence_lengths, prefix_lengths,
                                                                     block_ids, batch, max_blocks, tokens_per_block,
@@ -344,6 +415,11 @@ int b200_paged_decode_attn(const void* q, int is_bf16, void* out, size_t head_nu
               max_seq_len, max_blocks_per_seq * page_size);
     ARG_CHECK(batch * kv_head_num <= 65535, "paged_decode_attn: batch*kv_heads %zu exceeds grid limit", batch * kv_head_num);
     ARG_CHECK(((uintptr_t)kv_pool & 15) == 0 && ((uintptr_t)q & 3) == 0, "paged_decode_attn: misaligned pointer");
+    if (g_rec)
+        return rec_call([=](void* st) {
+            return b200_paged_decode_attn(q, is_bf16, out, head_num, kv_head_num, head_dim, batch, max_blocks_per_seq, max_seq_len,
+                                          page_size, kv_pool, page_list, sequence_lengths, q_scale, workspace, workspace_bytes, st);
+        });
 
     AttnParams p{};
     p.q = q;
@@ -385,7 +461,11 @@ int b200_paged_decode_attn(const void* q, int is_bf16, void* out, size_t head_nu
         if (rc) return rc;
     }
     const dim3 grid(p.nsplit, (unsigned)(batch * kv_head_num), 1);
-    static bool configured[2] = {false, false};
+    static bool configured_dev[16][2] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    ARG_CHECK(dev >= 0 && dev < 16, "device ordinal %d out of range", dev);
+    bool* configured = configured_dev[dev];
     if (is_bf16) {
         if (!configured[1]) {
             CUDA_CHECK(cudaFuncSetAttribute(paged_decode_attn_kernel<__nv_bfloat16>,
@@ -447,9 +527,11 @@ size_t b200_wo_gemm_workspace_bytes(int max_batch, int N, int K) {
     const int n_tiles = (N + kGemmTileN - 1) / kGemmTileN;
     int ns, kbp;
     gemm_split(n_tiles, K / kGemmBK, 16, &ns, &kbp);
-    // sized for the largest split the heuristic (or the env override) may pick for any batch <= max_batch
-    const size_t part = ns > 1 ? (size_t)ns * n_tiles * gemm_bpad(max_batch) * kGemmTileN * sizeof(float) : 0;
-    return kGemmSemBytes + part;
+    // sized for the largest split either GEMM path may pick for any batch <= max_batch
+    const int bpad = gemm_bpad(max_batch);
+    const size_t part = ns > 1 ? (size_t)ns * n_tiles * bpad * kGemmTileN * sizeof(float) : 0;
+    const size_t sk = sk_ws_bytes(n_tiles, K / kGemmBK, 2 * num_sms(), bpad);
+    return kGemmSemBytes + (part > sk ? part : sk);
 }
 
 int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const void* w, const void* col_scale,
@@ -463,9 +545,64 @@ int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const
     ARG_CHECK(fmt != B200_FMT_INT8 || col_scale, "wo_gemm: INT8 needs col_scale");
     ARG_CHECK((((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) == 0, "wo_gemm: x / w / y must be 16-byte aligned");
     const int n_tiles = (N + kGemmTileN - 1) / kGemmTileN;
-    ARG_CHECK((size_t)n_tiles * sizeof(int) <= kGemmSemBytes, "wo_gemm: N=%d too large", N);
+    ARG_CHECK((size_t)n_tiles * sizeof(int) <= kGemmSemBytes - 64, "wo_gemm: N=%d too large", N);
     const int bpad = gemm_bpad(B);
+    const bool silu_mul = (flags & B200_GEMM_SILU_MUL) != 0;
+    ARG_CHECK(!silu_mul || N % 128 == 0, "wo_gemm: SILU_MUL needs N %% 128 == 0 (gate/up interleaved per 128-feature tile)");
+    const bool use_pdl = (flags & B200_GEMM_PDL) || g_pdl.load();
 
+    CUtensorMap xmap;
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)B};
+        const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+        const cuuint32_t box[2] = {64, (cuuint32_t)bpad};
+        int rc = make_map(&xmap, is_bf16 != 0, 2, x, dims, strides, box);
+        if (rc) return rc;
+    }
+
+    // ---- weight-only INT8 / INT4 at decode batches: the persistent stream-K kernel (alone, or as one op of a program)
+    const bool streamk = fmt != B200_FMT_F16 && bpad <= 64 && !env_int("B200_GEMM_CLUSTERED", 0);
+    if (streamk) {
+        ARG_CHECK(workspace && workspace_bytes >= kGemmSemBytes, "wo_gemm: workspace of at least %zu bytes required", kGemmSemBytes);
+        int grid = 0;
+        int rc = segment_grid(is_bf16 != 0, bpad, fmt, &grid);
+        if (rc) return rc;
+        const SkPlan plan = sk_plan(n_tiles, K / kGemmBK, grid, bpad, workspace_bytes - kGemmSemBytes);
+        ProgOp op{};
+        op.xmap = xmap;
+        op.type = kOpGemm;
+        op.fmt = fmt;
+        SkGemmParams& g = op.g;
+        g.w_blob = reinterpret_cast<const uint8_t*>(w);
+        g.col_scale = col_scale;
+        g.bias = bias;
+        g.y = y;
+        g.B = B;
+        g.N = N;
+        g.K = K;
+        g.k_blocks = K / kGemmBK;
+        g.n_tiles = n_tiles;
+        g.total_kb = n_tiles * g.k_blocks;
+        g.per_cta = plan.per;
+        g.max_contrib = plan.max_contrib;
+        g.sem = reinterpret_cast<int*>(workspace);
+        g.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kGemmSemBytes);
+        g.silu_mul = silu_mul ? 1 : 0;
+        if (recording_fused(kOpGemm)) return rec_segment_op(op, is_bf16 ? 1 : 0, bpad, fmt);
+        if (g_rec)
+            return rec_call([=](void* st) {
+                return b200_wo_gemm(fmt, is_bf16, x, B, K, N, w, col_scale, bias, y, workspace, workspace_bytes, flags, st);
+            });
+        unsigned* gbar = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(workspace) + kGemmSemBytes - 64);
+        return launch_segment(is_bf16 != 0, bpad, fmt, &op, nullptr, 1, gbar, plan.used < grid ? plan.used : grid, use_pdl,
+                              nullptr, (cudaStream_t)stream);
+    }
+    if (g_rec)
+        return rec_call([=](void* st) {
+            return b200_wo_gemm(fmt, is_bf16, x, B, K, N, w, col_scale, bias, y, workspace, workspace_bytes, flags, st);
+        });
+
+    // ---- FP16 weights / batches above 64: one kernel per GEMM, cluster split-K (gemm_cluster.cu)
     GemmParams p{};
     p.w_blob = reinterpret_cast<const uint8_t*>(w);
     p.col_scale = col_scale;
@@ -475,10 +612,9 @@ int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const
     p.N = N;
     p.K = K;
     p.k_blocks = K / kGemmBK;
-    p.use_pdl = ((flags & B200_GEMM_PDL) || g_pdl.load()) ? 1 : 0;
-    p.silu_mul = (flags & B200_GEMM_SILU_MUL) ? 1 : 0;
-    ARG_CHECK(!p.silu_mul || N % 128 == 0, "wo_gemm: SILU_MUL needs N %% 128 == 0 (gate/up interleaved in 64-feature halves)");
-    p.dbg = env_int("B200_GEMM_DBG", 0);
+    p.use_pdl = use_pdl ? 1 : 0;
+    p.silu_mul = silu_mul ? 1 : 0;
+    p.dbg = 0;
 #ifdef B200_GEMM_DEV
     {
         const char* tr = getenv("B200_GEMM_TRACE_PTR");   // developer timeline buffer (device pointer)
@@ -507,15 +643,7 @@ int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const
             p.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kGemmSemBytes);
         }
     }
-
-    CUtensorMap xmap, wmap;
-    {
-        const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)B};
-        const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-        const cuuint32_t box[2] = {64, (cuuint32_t)bpad};
-        int rc = make_map(&xmap, is_bf16 != 0, 2, x, dims, strides, box);
-        if (rc) return rc;
-    }
+    CUtensorMap wmap;
     if (fmt == B200_FMT_F16) {
         const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
         const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
@@ -525,8 +653,7 @@ int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const
     } else {
         wmap = xmap;  // unused by the kernel
     }
-    if (is_bf16) return dispatch_gemm_fmt<__nv_bfloat16>(fmt, bpad, xmap, wmap, p, n_tiles, (cudaStream_t)stream);
-    return dispatch_gemm_fmt<__half>(fmt, bpad, xmap, wmap, p, n_tiles, (cudaStream_t)stream);
+    return launch_cluster_gemm(fmt, is_bf16 != 0, bpad, xmap, wmap, p, n_tiles, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------ glue ops
@@ -535,6 +662,19 @@ int b200_add_rmsnorm(const void* x, void* residual, const void* gamma, void* y, 
     if (rows == 0) return B200_OK;
     ARG_CHECK(x && gamma && y, "add_rmsnorm: null pointer");
     ARG_CHECK(hidden > 0 && hidden % 8 == 0 && hidden <= 12288, "add_rmsnorm: hidden=%d must be a multiple of 8, <= 12288", hidden);
+    if (recording_fused(kOpNorm) && hidden <= kSegNormMaxHidden) {
+        ProgOp op{};
+        op.type = kOpNorm;
+        op.n.x = x;
+        op.n.residual = residual;
+        op.n.gamma = gamma;
+        op.n.y = y;
+        op.n.rows = rows;
+        op.n.hidden = hidden;
+        op.n.eps = eps;
+        return rec_segment_op(op, is_bf16 ? 1 : 0, -1, -1);
+    }
+    if (g_rec) return rec_call([=](void* st) { return b200_add_rmsnorm(x, residual, gamma, y, is_bf16, rows, hidden, eps, st); });
     const int threads = hidden / 8 >= 512 ? 512 : (hidden / 8 >= 256 ? 256 : 128);
     const size_t smem = (size_t)hidden * sizeof(float);
     const bool pdl = g_pdl.load() != 0;
@@ -552,6 +692,7 @@ int b200_silu_and_mul(const void* gate_up, void* y, int is_bf16, int rows, int i
     if (rows == 0) return B200_OK;
     ARG_CHECK(gate_up && y, "silu_and_mul: null pointer");
     ARG_CHECK(inter > 0 && inter % 2 == 0, "silu_and_mul: inter=%d must be positive and even", inter);
+    if (g_rec) return rec_call([=](void* st) { return b200_silu_and_mul(gate_up, y, is_bf16, rows, inter, st); });
     const size_t total = (size_t)rows * inter / 2;
     const int threads = 256;
     const size_t blocks = (total + threads - 1) / threads;
@@ -573,8 +714,30 @@ int b200_rope_append(const void* qkv, void* q_out, void* kv_pool, const int32_t*
     ARG_CHECK(qkv && q_out && kv_pool && page_list && sequence_lengths, "rope_append: null pointer");
     ARG_CHECK(head_dim > 0 && head_dim % 2 == 0 && head_dim <= 512, "rope_append: head_dim %d unsupported", head_dim);
     ARG_CHECK(rope_base > 1.f, "rope_append: rope_base must be > 1");
-    const dim3 grid(batch, head_num + 2 * kv_head_num);
     const float l2b = std::log2(rope_base);
+    if (recording_fused(kOpRope)) {
+        ProgOp op{};
+        op.type = kOpRope;
+        op.r.qkv = qkv;
+        op.r.q_out = q_out;
+        op.r.kv_pool = kv_pool;
+        op.r.page_list = page_list;
+        op.r.seq_lens = sequence_lengths;
+        op.r.B = batch;
+        op.r.head_num = head_num;
+        op.r.kv_head_num = kv_head_num;
+        op.r.head_dim = head_dim;
+        op.r.max_blocks = max_blocks_per_seq;
+        op.r.page_size = page_size;
+        op.r.log2_base = l2b;
+        return rec_segment_op(op, is_bf16 ? 1 : 0, -1, -1);
+    }
+    if (g_rec)
+        return rec_call([=](void* st) {
+            return b200_rope_append(qkv, q_out, kv_pool, page_list, sequence_lengths, is_bf16, batch, head_num, kv_head_num,
+                                    head_dim, max_blocks_per_seq, page_size, rope_base, st);
+        });
+    const dim3 grid(batch, head_num + 2 * kv_head_num);
     const bool pdl = g_pdl.load() != 0;
     if (is_bf16)
         CUDA_CHECK(launch_ex(rope_append_kernel<__nv_bfloat16>, grid, dim3(head_dim / 2), 0, (cudaStream_t)stream, pdl,
@@ -592,6 +755,17 @@ int b200_embedding(const int32_t* ids, const void* table, void* out, int is_bf16
     if (rows == 0) return B200_OK;
     ARG_CHECK(ids && table && out, "embedding: null pointer");
     ARG_CHECK(hidden > 0 && hidden % 8 == 0, "embedding: hidden=%d must be a multiple of 8", hidden);
+    if (recording_fused(kOpEmbed)) {
+        ProgOp op{};
+        op.type = kOpEmbed;
+        op.e.ids = ids;
+        op.e.table = table;
+        op.e.out = out;
+        op.e.rows = rows;
+        op.e.hidden = hidden;
+        return rec_segment_op(op, -1, -1, -1);
+    }
+    if (g_rec) return rec_call([=](void* st) { return b200_embedding(ids, table, out, is_bf16, rows, hidden, st); });
     embedding_kernel<__half><<<rows, 128, 0, (cudaStream_t)stream>>>(ids, (const __half*)table, (__half*)out, hidden);
     return launched("embedding_kernel");
 }
@@ -601,6 +775,7 @@ int b200_argmax(const void* logits, int dtype, int rows, int vocab, int32_t* out
     ARG_CHECK(logits && out, "argmax: null pointer");
     ARG_CHECK(vocab > 0, "argmax: vocab must be positive");
     ARG_CHECK(dtype >= 0 && dtype <= 2, "argmax: dtype %d unknown (0 fp16, 1 bf16, 2 fp32)", dtype);
+    if (g_rec) return rec_call([=](void* st) { return b200_argmax(logits, dtype, rows, vocab, out, st); });
     if (dtype == 0)
         argmax_kernel<__half><<<rows, 1024, 0, (cudaStream_t)stream>>>((const __half*)logits, vocab, out);
     else if (dtype == 1)
@@ -646,6 +821,12 @@ int b200_peer_allreduce(const void* in, void* out, size_t bytes, int is_bf16, vo
     ARG_CHECK(world >= 2 && world <= kArMaxWorld && rank >= 0 && rank < world, "peer_allreduce: bad rank/world %d/%d", rank, world);
     ARG_CHECK(bytes > 0 && bytes % 16 == 0 && bytes <= max_message_bytes, "peer_allreduce: message of %zu bytes unsupported", bytes);
     ARG_CHECK((((uintptr_t)in | (uintptr_t)out) & 15) == 0, "peer_allreduce: in/out must be 16-byte aligned");
+    if (g_rec) {
+        std::vector<void*> regs(regions, regions + world);
+        return rec_call([=](void* st) {
+            return b200_peer_allreduce(in, out, bytes, is_bf16, regs.data(), max_message_bytes, call_parity, rank, world, st);
+        });
+    }
     const size_t src_stride = 2 * round_up(max_message_bytes, 256);          // LL doubles the bytes
     const size_t area_stride = (size_t)kArMaxWorld * src_stride;
     const size_t parity_stride = 2 * area_stride;
@@ -689,38 +870,76 @@ int b200_peer_allreduce(const void* in, void* out, size_t bytes, int is_bf16, vo
     return launched("peer_allreduce_kernel");
 }
 
-// ------------------------------------------------------------------------------------------------ GPU-side checkers
-int b200_ref_paged_decode_attn(const void* q, int is_bf16, void* out, int head_num, int kv_head_num, int head_dim,
-                               int batch, int max_blocks_per_seq, int page_size, const void* kv_pool,
-                               const int32_t* page_list, const int32_t* sequence_lengths, float q_scale, void* stream) {
-    if (batch == 0) return B200_OK;
-    ARG_CHECK(head_dim % 32 == 0 && head_dim <= 256, "ref attn: head_dim %d unsupported", head_dim);
-    const dim3 grid(batch, head_num);
-    const float scale = q_scale / std::sqrt((float)head_dim);
-    if (is_bf16)
-        ref_paged_decode_attn_kernel<__nv_bfloat16><<<grid, 32, 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16*)q, (__nv_bfloat16*)out, (const __nv_bfloat16*)kv_pool, page_list, sequence_lengths,
-            head_num, kv_head_num, head_dim, max_blocks_per_seq, page_size, scale);
-    else
-        ref_paged_decode_attn_kernel<__half><<<grid, 32, 0, (cudaStream_t)stream>>>(
-            (const __half*)q, (__half*)out, (const __half*)kv_pool, page_list, sequence_lengths, head_num, kv_head_num,
-            head_dim, max_blocks_per_seq, page_size, scale);
-    return launched("ref_paged_decode_attn_kernel");
+// ------------------------------------------------------------------------------------------------ decode programs
+int b200_program_create(b200_program** out) {
+    ARG_CHECK(out, "program_create: null pointer");
+    *out = new b200_program();
+    (*out)->fuse = env_int("B200_PROGRAM_FUSE", 1) != 0;
+    return B200_OK;
 }
 
-int b200_ref_dequant_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const void* w, const void* scales,
-                          const void* zeros_x_scales, int group, const void* bias, void* y, void* stream) {
-    if (B == 0) return B200_OK;
-    const dim3 grid((N + 127) / 128, B);
-    if (is_bf16)
-        ref_dequant_gemm_kernel<__nv_bfloat16><<<grid, 128, 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16*)x, B, K, N, fmt, w, (const __nv_bfloat16*)scales, (const __nv_bfloat16*)zeros_x_scales,
-            group, (const __nv_bfloat16*)bias, (__nv_bfloat16*)y);
-    else
-        ref_dequant_gemm_kernel<__half><<<grid, 128, 0, (cudaStream_t)stream>>>(
-            (const __half*)x, B, K, N, fmt, w, (const __half*)scales, (const __half*)zeros_x_scales, group,
-            (const __half*)bias, (__half*)y);
-    return launched("ref_dequant_gemm_kernel");
+int b200_program_begin(b200_program* p) {
+    ARG_CHECK(p && !p->finalized, "program_begin: null or already finalised program");
+    ARG_CHECK(!g_rec, "program_begin: this thread is already recording a program");
+    g_rec = p;
+    return B200_OK;
+}
+
+int b200_program_end(b200_program* p) {
+    ARG_CHECK(p && g_rec == p, "program_end: this thread is not recording this program");
+    g_rec = nullptr;
+    if (!p->ops.empty()) {
+        CUDA_CHECK(cudaMalloc(&p->d_ops, p->ops.size() * sizeof(ProgOp)));
+        CUDA_CHECK(cudaMemcpy(p->d_ops, p->ops.data(), p->ops.size() * sizeof(ProgOp), cudaMemcpyHostToDevice));
+    }
+    const size_t bar_bytes = (p->items.size() + 1) * 256;
+    CUDA_CHECK(cudaMalloc(&p->d_bar, bar_bytes));
+    CUDA_CHECK(cudaMemset(p->d_bar, 0, bar_bytes));
+    CUDA_CHECK(cudaDeviceSynchronize());
+    p->finalized = true;
+    return B200_OK;
+}
+
+int b200_program_set_trace(b200_program* p, void* device_buffer) {
+    ARG_CHECK(p, "program_set_trace: null program");
+    p->trace = reinterpret_cast<unsigned long long*>(device_buffer);
+    return B200_OK;
+}
+
+int b200_program_num_ops(const b200_program* p) { return p ? (int)p->ops.size() : 0; }
+int b200_program_num_launches(const b200_program* p) { return p ? (int)p->items.size() : 0; }
+
+int b200_program_launch(b200_program* p, void* stream) {
+    ARG_CHECK(p && p->finalized, "program_launch: program not finalised (b200_program_end)");
+    ARG_CHECK(!g_rec, "program_launch: cannot launch while recording");
+    const bool pdl = g_pdl.load() != 0;
+    for (size_t i = 0; i < p->items.size(); ++i) {
+        const b200_program::Item& it = p->items[i];
+        int rc;
+        if (it.segment) {
+            const bool bf16 = it.bf16 > 0;
+            const int bpad = it.bpad > 0 ? it.bpad : 32, qfmt = it.qfmt > 0 ? it.qfmt : B200_FMT_INT4;
+            int grid = 0;
+            rc = segment_grid(bf16, bpad, qfmt, &grid);
+            if (rc) return rc;
+            unsigned long long* tr = p->trace ? p->trace + (size_t)it.first * grid * 2 : nullptr;
+            rc = launch_segment(bf16, bpad, qfmt, nullptr, p->d_ops + it.first, it.count, p->d_bar + i * 64, grid, pdl, tr,
+                                (cudaStream_t)stream);
+        } else {
+            rc = it.fn(stream);
+        }
+        if (rc) return rc;
+    }
+    return B200_OK;
+}
+
+int b200_program_destroy(b200_program* p) {
+    if (!p) return B200_OK;
+    if (g_rec == p) g_rec = nullptr;
+    if (p->d_ops) cudaFree(p->d_ops);
+    if (p->d_bar) cudaFree(p->d_bar);
+    delete p;
+    return B200_OK;
 }
 
 }  // extern "C"

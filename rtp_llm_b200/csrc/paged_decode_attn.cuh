@@ -59,7 +59,9 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
     pdl_launch_dependents();   // let the o-projection GEMM start prefetching its weights
     pdl_wait();                // q and the appended K/V come from the previous kernel
 
-    const int len = p.seq_lens[b] + 1;
+    // the host sized the split for max_seq_len: a longer sequence is clamped to that bound (never more tiles than the
+    // splits cover, so the last-arriver count below always matches the CTAs that really contribute)
+    const int len = min(p.seq_lens[b] + 1, p.nsplit * p.tiles_per_split * kAttnTile);
     const int ntiles = (len + kAttnTile - 1) / kAttnTile;
     const int t0 = split * p.tiles_per_split;
     const int t1 = min(t0 + p.tiles_per_split, ntiles);

@@ -79,6 +79,59 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+
+// ---- the same primitives on raw 32-bit shared addresses (a persistent kernel keeps ONE base register and constant
+// offsets instead of a dozen 64-bit generic pointers)
+__device__ __forceinline__ void mbar_init_a(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// liveness guard: 2^22 failed try_waits (each suspends up to the hardware time limit; seconds in total) is far beyond any
+// legitimate wait; a protocol bug then traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_a(bar, parity)) {
+        if (++spins > (1u << 22)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d_a(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_load_a(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+                 "l"(gsrc), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
+
 // ---------------------------------------------------------------- TMA
 // 4-D tiled tensor load (global -> shared), completion on an mbarrier (complete_tx::bytes).
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
@@ -261,6 +314,13 @@ __device__ __forceinline__ void umma_ss_f16(uint32_t d_tmem, uint64_t a_desc, ui
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+}
+
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_a(uint32_t smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot), "r"(ncols) : "memory");
 }
 
 // Instruction descriptor for kind::f16 (bit layout: cute/arch/mma_sm100_desc.hpp InstrDescriptor semantics restated):

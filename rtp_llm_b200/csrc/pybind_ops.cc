@@ -113,7 +113,7 @@ public:
         update_offset_tensor(params->kv_cache_offset, block_ids);
         params->batch_size = (size_t)batch;
         const size_t cap = (size_t)block_ids.size(1) * page_size_of(attn_configs_);
-        params->max_seq_len = attn_configs_.max_seq_len < cap ? attn_configs_.max_seq_len : cap;
+        params->max_seq_len = attn_configs_.max_seq_len + 1 < cap ? attn_configs_.max_seq_len + 1 : cap;   // XQAAttnOp.cc:147-149 passes max_seq_len + 1
         params->sequence_lengths = attn_inputs.sequence_lengths;
         const size_t ws = b200_paged_decode_attn_workspace_bytes(params->batch_size, attn_configs_.head_num,
                                                                  attn_configs_.kv_head_num, params->max_seq_len);

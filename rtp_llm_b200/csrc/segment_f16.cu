@@ -1,0 +1,7 @@
+#include "segment_inst.cuh"
+namespace b200_host {
+int seg_dispatch_f16(int bpad, int qfmt, const ProgOp* op0, const ProgOp* d_ops, int nops, unsigned* gbar, int grid, bool pdl,
+                     unsigned long long* trace, cudaStream_t st, int* grid_out) {
+    return seg_dispatch<__half>(bpad, qfmt, op0, d_ops, nops, gbar, grid, pdl, trace, st, grid_out);
+}
+}  // namespace b200_host

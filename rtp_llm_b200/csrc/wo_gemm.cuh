@@ -89,7 +89,7 @@ struct GemmParams {
     float* ws;               // [nsplit][n_tiles][bpad][128] fp32 split-K partials
     int* sem;                // [n_tiles], zero on entry / exit
     int use_pdl;
-    int silu_mul;            // 1: tile rows 0-63 are gate features, rows 64-127 the matching up features; y[b][tile*64+r] = silu(g)*u
+    int silu_mul;            // 1: tile rows 2r / 2r+1 are gate / up feature tile*64+r; y[b][tile*64+r] = silu(g)*u
     int cluster_reduce;      // 1: the nsplit CTAs of a tile form a cluster (1,nsplit,1) and merge through DSMEM
     long long* trace;        // developer timeline (tools/gemm_trace.py); null in production
     int dbg;                 // developer experiments (env B200_GEMM_DBG): 1 no math, 2 no TMEM store, 4 no MMA; 0 in production
@@ -659,7 +659,7 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
                 if (b >= p.B || (b % S) != rank) continue;      // with a cluster merge each CTA owns the columns b % S == rank
                 const int j = tile * 64 + r;
                 if (j >= n_out) continue;
-                const float g = fin[b * kGemmTileN + r], u = fin[b * kGemmTileN + 64 + r];
+                const float g = fin[b * kGemmTileN + 2 * r], u = fin[b * kGemmTileN + 2 * r + 1];   // rows 2r / 2r+1 = gate / up pair
                 yp[(size_t)b * n_out + j] = from_f32<T>(g / (1.f + __expf(-g)) * u);
             }
         }
@@ -688,7 +688,7 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
 // ---- load-time re-layout kernels (replace device_impl.py:392-479 preprocess_weights_for_mixed_gemm): reference
 // (un-permuted) tensors -> per-(n-tile, k-block) blobs consumed above.
 // int4: q_packed [K][N/2] (byte = hi nibble col 2j+1, lo nibble col 2j, two's complement q_s), scales/zs [K/128][N] (16-bit).
-__global__ void pack_w4_kernel(const uint8_t* __restrict__ q_packed, const uint16_t* __restrict__ scales,
+static __global__ void pack_w4_kernel(const uint8_t* __restrict__ q_packed, const uint16_t* __restrict__ scales,
                                const uint16_t* __restrict__ zs, int K, int N, uint8_t* __restrict__ blob) {
     const int k_blocks = K / kGemmBK;
     const int n_tiles = (N + kGemmTileN - 1) / kGemmTileN;
@@ -728,7 +728,7 @@ __global__ void pack_w4_kernel(const uint8_t* __restrict__ q_packed, const uint1
     }
 }
 // int8: q [K][N] int8 -> blobs of u = q + 128
-__global__ void pack_w8_kernel(const int8_t* __restrict__ q, int K, int N, uint8_t* __restrict__ blob) {
+static __global__ void pack_w8_kernel(const int8_t* __restrict__ q, int K, int N, uint8_t* __restrict__ blob) {
     const int k_blocks = K / kGemmBK;
     const int n_tiles = (N + kGemmTileN - 1) / kGemmTileN;
     const size_t total = (size_t)n_tiles * k_blocks * kW8BlockBytes;

@@ -199,6 +199,7 @@ class DecodeStep:
         self.attn_ws = ops.attn_workspace(batch, self.Hq, self.Hkv, ctx, device)
         ops.set_pdl(pdl)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.prog = None
         self.upload_inputs()
         torch.cuda.synchronize(device)
 
@@ -223,7 +224,8 @@ class DecodeStep:
         if self.tp_size > 1:
             self.comm.all_reduce(t)
 
-    def step(self):
+    def step_core(self):
+        """Everything up to the (local) logits: only C-ABI calls, so it can be recorded into a decode program."""
         cfg = self.cfg
         ops.convert_block_table(self.block_ids, out=self.page_list)
         ops.embedding(self.ids, self.embed, out=self.resid)
@@ -249,16 +251,42 @@ class DecodeStep:
             self._all_reduce(self.proj)
         ops.add_rmsnorm(self.proj, self.resid, self.final_ln, cfg.eps, out=self.x)
         ops.wo_gemm(self.x, self.lm_head, self.gemm_ws, out=self.logits, pdl=self.pdl)
+        if self.tp_size == 1:
+            ops.argmax(self.logits, out=self.next_ids)
+
+    def step_tail(self):
+        """TP > 1: gather the vocab-split logits and sample (torch / NCCL plumbing, outside the program)."""
         if self.tp_size > 1:
             self.comm.all_gather(self.logits_all, self.logits)
             full = self.logits_all.permute(1, 0, 2).reshape(self.B, -1)[:, : self.cfg.vocab]   # drop the sp_0_pad8 columns
-            self.next_ids.copy_(torch.argmax(full.float(), dim=-1).to(torch.int32))  # next: own kernel over the gathered view
+            self.next_ids.copy_(torch.argmax(full.float(), dim=-1).to(torch.int32))
+
+    def step(self):
+        """One decode step, op by op (one kernel per call)."""
+        self.step_core()
+        self.step_tail()
+
+    def build_program(self):
+        """Record step_core() into a decode program (b200_program_*): the ops between two attention calls become one
+        persistent-kernel launch. Requires every call in step_core to go through the C ABI (own peer all-reduce, not NCCL)."""
+        from . import tp as tpmod
+        assert self.tp_size == 1 or isinstance(self.comm, tpmod.PeerComm), "a program cannot record NCCL calls"
+        self.prog = ops.Program()
+        with self.prog.record():
+            self.step_core()
+        return self.prog
+
+    def run(self):
+        """One decode step through the program if one was built, else op by op."""
+        if getattr(self, "prog", None) is not None:
+            self.prog.launch()
+            self.step_tail()
         else:
-            ops.argmax(self.logits, out=self.next_ids)
+            self.step()
 
     def launches_per_step(self) -> int:
         n0 = ops.launch_count()
-        self.step()
+        self.run()
         return ops.launch_count() - n0
 
     def capture(self):
@@ -266,12 +294,12 @@ class DecodeStep:
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):
             for _ in range(2):
-                self.step()
+                self.run()
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.step()
+            self.run()
         torch.cuda.synchronize(self.dev)
 
     def replay(self):

@@ -142,19 +142,22 @@ def gemm_workspace(max_batch: int, shapes, device) -> torch.Tensor:
 
 
 def gate_up_order(inter: int, device=None) -> torch.Tensor:
-    """Column order that puts, for every 64 outputs j, [gate j .. j+63 | up j .. j+63] into one 128-feature tile: the
-    layout the fused SiLU*mul epilogue (B200_GEMM_SILU_MUL) expects of a [K, 2*inter] gate|up weight."""
+    """Column order that puts gate j and up j into ADJACENT rows of a 128-feature tile (row 2i = gate tile*64+i, row 2i+1 =
+    up tile*64+i): the layout the fused SiLU*mul epilogue (B200_GEMM_SILU_MUL) expects of a [K, 2*inter] gate|up weight --
+    the two values of a pair then sit in neighbouring lanes of one warp and are exchanged with a shuffle."""
     assert inter % 64 == 0
-    j = torch.arange(inter, device=device).reshape(-1, 64)
-    return torch.cat([j, j + inter], dim=1).reshape(-1)
+    j = torch.arange(inter, device=device)
+    return torch.stack([j, j + inter], dim=1).reshape(-1)
 
 
 def interleave_gate_up(w: torch.Tensor, inter: int, packed_int4: bool = False) -> torch.Tensor:
-    """Apply gate_up_order to the column axis of a reference-layout tensor ([K, 2I], or uint8 [K, I] packed int4,
-    or scales [G, 2I] / [2I])."""
+    """Apply gate_up_order to the column axis of a reference-layout tensor ([K, 2I], or uint8 [K, I] packed int4 -- low
+    nibble = even column --, or scales [G, 2I] / [2I])."""
     order = gate_up_order(inter, w.device)
     if packed_int4:
-        order = order.reshape(-1, 2)[:, 0] // 2          # byte index of every column pair (64 is even)
+        full = torch.stack([w & 0xF, w >> 4], dim=-1).reshape(w.shape[0], -1)       # one nibble per column [K, 2I]
+        full = full.index_select(-1, order)
+        return (full[:, 0::2] | (full[:, 1::2] << 4)).contiguous()
     return w.index_select(-1, order).contiguous()
 
 
@@ -225,23 +228,54 @@ def argmax(logits, out=None):
     return out
 
 
-# ------------------------------------------------------------------------------------------------ GPU-side checkers (tests only)
-def ref_paged_decode_attn(q, kv_cache_base, page_list, sequence_lengths, q_scale=1.0):
-    P, two, Hkv, T, D = kv_cache_base.shape
-    B = q.shape[0]
-    Hq = q.numel() // (B * D)
-    out = torch.empty((B, Hq * D), dtype=q.dtype, device=q.device)
-    check(_lib.load().b200_ref_paged_decode_attn(_p(q), _is_bf16(q), _p(out), Hq, Hkv, D, B, page_list.shape[-1], T,
-                                                 _p(kv_cache_base), _p(page_list), _p(sequence_lengths), q_scale,
-                                                 _stream()), "b200_ref_paged_decode_attn")
-    return out
+# ------------------------------------------------------------------------------------------------ decode programs
+class Program:
+    """Recorded sequence of op calls (b200_program_*): `with prog.record(): <ops...>` then `prog.launch()` replays them
+    with the GEMMs / norms / rope between two attention calls fused into one persistent kernel. Pointers are frozen at
+    record time (like a CUDA-graph capture); launch() is itself graph-capturable."""
 
+    def __init__(self):
+        import ctypes
+        self._h = ctypes.c_void_p()
+        check(_lib.load().b200_program_create(ctypes.byref(self._h)), "b200_program_create")
+        self._keep = []
 
-def ref_dequant_gemm(x, fmt, w, scales=None, zeros_x_scales=None, group=128, bias=None):
-    """fmt F16: w [K,N]; INT8: w int8 [K,N] + scales [N]; INT4: w uint8 [K,N/2] + scales/zeros [K/g,N]."""
-    B, K = x.shape
-    N = w.shape[1] * (2 if fmt == B200_FMT_INT4 else 1)
-    out = torch.empty((B, N), dtype=x.dtype, device=x.device)
-    check(_lib.load().b200_ref_dequant_gemm(fmt, _is_bf16(x), _p(x), B, K, N, _p(w), _p(scales), _p(zeros_x_scales), group,
-                                            _p(bias), _p(out), _stream()), "b200_ref_dequant_gemm")
-    return out
+    class _Rec:
+        def __init__(self, prog):
+            self.prog = prog
+
+        def __enter__(self):
+            check(_lib.load().b200_program_begin(self.prog._h), "b200_program_begin")
+            return self.prog
+
+        def __exit__(self, et, ev, tb):
+            rc = _lib.load().b200_program_end(self.prog._h)
+            if et is None:
+                check(rc, "b200_program_end")
+            return False
+
+    def record(self):
+        return Program._Rec(self)
+
+    def launch(self) -> None:
+        check(_lib.load().b200_program_launch(self._h, _stream()), "b200_program_launch")
+
+    @property
+    def num_ops(self) -> int:
+        return int(_lib.load().b200_program_num_ops(self._h))
+
+    @property
+    def num_launches(self) -> int:
+        return int(_lib.load().b200_program_num_launches(self._h))
+
+    def set_trace(self, buf: Optional[torch.Tensor]) -> None:
+        self._keep.append(buf)
+        check(_lib.load().b200_program_set_trace(self._h, _p(buf)), "b200_program_set_trace")
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.load().b200_program_destroy(self._h)
+                self._h = None
+        except Exception:  # noqa: BLE001
+            pass

@@ -48,17 +48,20 @@ def oracle_step(model: DecodeStep, kv_before):
     return orc.from_bits(logits, False)
 
 
-def check_tiny_step(dev, quant="int4", batch=3, ctx=40, graph=False, pdl=False) -> float:
+def check_tiny_step(dev, quant="int4", batch=3, ctx=40, graph=False, pdl=False, program=False) -> float:
     cfg = dataclasses.replace(TINY, quant=quant)
     model = DecodeStep(cfg, batch, ctx, dev, keep_reference=True, ragged=True, seed=1, pdl=pdl)
     kv_before = [_bits(L["kv"]) for L in model.layers]
+    if program:
+        model.build_program()
+        assert model.prog.num_ops > 0, "nothing was fused into the persistent kernel"
     if graph:
         for L, kb in zip(model.layers, kv_before):   # capture() runs the step (appends K/V): the append is idempotent
             pass
         model.capture()
         model.replay()
     else:
-        model.step()
+        model.run()
     torch.cuda.synchronize(dev)
     if pdl:
         from rtp_llm_b200 import ops

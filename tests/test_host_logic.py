@@ -111,18 +111,22 @@ def test_algorithmic_bytes_match_baseline_md():
 
 
 def test_gate_up_interleave_order():
-    """ops.gate_up_order: every 128-column tile = [64 gate columns j.. | the 64 up columns j..] (fused SiLU*mul layout)."""
+    """ops.gate_up_order: rows 2i / 2i+1 of every 128-column tile = gate / up column tile*64+i (fused SiLU*mul layout: the
+    pair sits in neighbouring lanes of one warp)."""
     from rtp_llm_b200 import ops
     inter = 192
     order = ops.gate_up_order(inter)
     assert sorted(order.tolist()) == list(range(2 * inter))
     for t in range(inter // 64):
         tile = order[t * 128:(t + 1) * 128]
-        assert tile[:64].tolist() == list(range(t * 64, t * 64 + 64))
-        assert tile[64:].tolist() == list(range(inter + t * 64, inter + t * 64 + 64))
+        assert tile[0::2].tolist() == list(range(t * 64, t * 64 + 64))
+        assert tile[1::2].tolist() == list(range(inter + t * 64, inter + t * 64 + 64))
     w = torch.arange(2 * inter).repeat(3, 1)
     assert torch.equal(ops.interleave_gate_up(w, inter)[0], order)
-    # packed int4: bytes hold column pairs, so the byte order is the pair order
-    packed = (torch.arange(inter) * 1).to(torch.uint8).repeat(2, 1)          # byte j <-> columns (2j, 2j+1)
-    got = ops.interleave_gate_up(packed, inter, packed_int4=True)[0].long()
-    assert got.tolist() == (order.reshape(-1, 2)[:, 0] // 2).tolist()
+    # packed int4 (low nibble = even column): unpack -> reorder -> repack must equal reordering the nibble matrix
+    g = torch.Generator().manual_seed(0)
+    packed = torch.randint(0, 256, (2, inter), generator=g, dtype=torch.uint8)
+    nib = torch.stack([packed & 0xF, packed >> 4], dim=-1).reshape(2, -1)
+    got = ops.interleave_gate_up(packed, inter, packed_int4=True)
+    got_nib = torch.stack([got & 0xF, got >> 4], dim=-1).reshape(2, -1)
+    assert torch.equal(got_nib, nib.index_select(-1, order))

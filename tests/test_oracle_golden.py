@@ -136,3 +136,28 @@ def test_rope_append_roundtrip_properties():
     np.testing.assert_array_equal(pool2[block_ids[1, 2], 1, :, 37 % 16, :], v)
     # nothing else written
     assert np.count_nonzero(pool2) <= 2 * 2 * Hkv * D
+
+
+@pytest.mark.parametrize("name", ["rope_base10000", "rope_base500000", "rope_d64"])
+def test_rope_matches_reference_torch_rope(golden_dir, name):
+    """oracle_rope_append pinned to the reference's own pure-torch RoPE (create_cos_sin_cache + apply_rope_reference,
+    test_mha_rotary_emb.py:47-81,121-165; fixtures by oracle/make_golden.py). Tolerance = the reference test's
+    rtol = atol = 1e-2 (:506-507); V must be appended unrotated, bit for bit."""
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    qkv = g["qkv"]
+    B = qkv.shape[0]
+    Hq, Hkv, D = int(g["head_num"]), int(g["kv_head_num"]), int(g["head_dim"])
+    pos = g["positions"].astype(np.int32)
+    T = 16
+    M = int(pos.max()) // T + 1
+    block_ids = (np.arange(B * M, dtype=np.int32) + 1).reshape(B, M)
+    pl = orc.convert_block_table(block_ids)
+    pool = np.zeros((1 + B * M, 2, Hkv, T, D), np.float16)
+    q_out, pool_out = orc.rope_append(qkv.view(np.uint16), pool.view(np.uint16), pl, pos, Hq, Hkv, D, T, float(g["rope_base"]))
+    np.testing.assert_allclose(orc.from_bits(q_out, False).reshape(B, Hq, D), g["q_rope"].astype(np.float32), rtol=1e-2, atol=1e-2)
+    pool_f = pool_out.view(np.float16).reshape(pool.shape)
+    for b in range(B):
+        page, slot = block_ids[b, pos[b] // T], pos[b] % T
+        np.testing.assert_allclose(pool_f[page, 0, :, slot].astype(np.float32), g["k_rope"][b].astype(np.float32), rtol=1e-2, atol=1e-2)
+        v = qkv[b, (Hq + Hkv) * D:].reshape(Hkv, D)
+        assert np.array_equal(pool_f[page, 1, :, slot], v)

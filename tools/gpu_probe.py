@@ -15,6 +15,7 @@ sys.path.insert(0, ROOT)
 from oracle import oracle as orc  # noqa: E402
 from rtp_llm_b200 import ops  # noqa: E402
 from rtp_llm_b200._lib import B200_FMT_F16, B200_FMT_INT4, B200_FMT_INT8  # noqa: E402
+from tests import ref_kernels as refk  # noqa: E402  (naive CUDA-core second opinion, test-only library)
 
 dev = torch.device("cuda:0")
 RESULTS = []
@@ -72,7 +73,7 @@ def run_attn(q, pool, block_ids, seq, max_len=None):
     max_len = max_len or int(seq.max().item()) + 1
     ws = ops.attn_workspace(B, Hq, pool.shape[2], max_len, dev)
     out = ops.paged_decode_attn(qd, poold, pl, sd, max_len, ws)
-    ref = ops.ref_paged_decode_attn(qd, poold, pl, sd)
+    ref = refk.ref_paged_decode_attn(qd, poold, pl, sd)
     torch.cuda.synchronize()
     return out, ref, ws
 
@@ -107,11 +108,19 @@ def attn_vs_oracle(name, B, Hq, Hkv, T, lens, dtype=torch.float16, env=None):
 
 
 def attn_vs_ref_big(name, B, Hq, Hkv, T, S, dtype=torch.float16, ragged=False):
+    """BASELINE-size shapes: the CPU oracle is the checker (it finishes these in well under a second per case with
+    OpenMP); the naive GPU kernel is kept as a second opinion."""
     def fn():
         rng = np.random.default_rng(4)
         lens = [int(x) for x in (rng.integers(S // 2, S + 1, B) if ragged else [S] * B)]
         q, pool, block_ids, seq = make_attn_case(B, Hq, Hkv, T, lens, dtype, seed=42)
         out, ref, _ = run_attn(q, pool, block_ids, seq, max_len=S)
+        is_bf16 = dtype == torch.bfloat16
+        bits = lambda t: t.view(torch.int16).numpy().view(np.uint16)
+        exp = orc.from_bits(orc.paged_decode_attn(bits(q), bits(pool), orc.convert_block_table(block_ids.numpy()),
+                                                  seq.numpy(), Hq, Hkv, 128, T, is_bf16=is_bf16), is_bf16)
+        ok, info = diff_info(out, exp, 1e-2, 1e-2)
+        report(name + " [kernel vs oracle]", ok, info)
         ok, info = diff_info(out, ref.float().cpu().numpy(), 1e-2, 1e-2)
         report(name + " [kernel vs ref-kernel]", ok, info)
     guard(name, fn)
@@ -153,7 +162,7 @@ def gemm_case(name, fmt, B, K, N, dtype=torch.float16, simple=False, onehot=Fals
                 qd = torch.from_numpy(qp).to(dev)
                 sd, zd = torch.from_numpy(s).to(dtype).to(dev), torch.from_numpy(zs).to(dtype).to(dev)
                 w = ops.pack_w4(qd, sd, zd)
-                ref = ops.ref_dequant_gemm(x, fmt, qd, sd, zd, 128, bias_t)
+                ref = refk.ref_dequant_gemm(x, fmt, qd, sd, zd, 128, bias_t)
             elif fmt == B200_FMT_INT8:
                 q8 = rng.integers(-128, 128, (K, N)).astype(np.int8)
                 # realistic magnitude: W' ~ N(0, 0.02) like the loader's scale = amax/128 (device_impl.py:190)
@@ -162,12 +171,12 @@ def gemm_case(name, fmt, B, K, N, dtype=torch.float16, simple=False, onehot=Fals
                     s[:] = 1.0
                 qd, sd = torch.from_numpy(q8).to(dev), torch.from_numpy(s).to(dtype).to(dev)
                 w = ops.pack_w8(qd, sd)
-                ref = ops.ref_dequant_gemm(x, fmt, qd, sd, None, 128, bias_t)
+                ref = refk.ref_dequant_gemm(x, fmt, qd, sd, None, 128, bias_t)
             else:
                 wf = (rng.standard_normal((K, N)) * 0.05).astype(np.float32)
                 wd = torch.from_numpy(wf).to(dtype).to(dev)
                 w = ops.pack_f16(wd)
-                ref = ops.ref_dequant_gemm(x, fmt, wd, None, None, 128, bias_t)
+                ref = refk.ref_dequant_gemm(x, fmt, wd, None, None, 128, bias_t)
             ws = ops.gemm_workspace(max(B, 1), [(K, N)], dev)
             y = ops.wo_gemm(x, w, ws, bias=bias_t)
             torch.cuda.synchronize()
@@ -176,7 +185,7 @@ def gemm_case(name, fmt, B, K, N, dtype=torch.float16, simple=False, onehot=Fals
                 tol = 4e-2
             ok, info = diff_info(y, ref.float().cpu().numpy(), tol, tol * (1 if not simple else 1))
             report(name + " [kernel vs ref-kernel]", ok, info)
-            if not big and not onehot:
+            if not onehot:     # every size, BASELINE shapes included: the CPU oracle is the checker
                 bits = lambda t: t.cpu().view(torch.int16).numpy().view(np.uint16)
                 is_bf16 = dtype == torch.bfloat16
                 if fmt == B200_FMT_INT4:
