@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--ctx", type=int, default=2048)
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("B200_PDL", "1")))  # programmatic dependent launch (bit-identical results)
-    ap.add_argument("--program", type=int, default=int(os.environ.get("B200_PROGRAM", "1")))  # record the step into a decode program (persistent kernel between attention calls)
+    ap.add_argument("--program", type=int, default=int(os.environ.get("B200_PROGRAM", "0")))  # record the step into a decode program (persistent kernel between attention calls)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--comm", default=os.environ.get("B200_COMM", "peer"), choices=["peer", "nccl"])
     return ap.parse_args()

@@ -29,6 +29,7 @@ using namespace b200_host;
 namespace b200_host {
 
 thread_local std::string g_err;
+thread_local unsigned long long* g_ftrace_next = nullptr;
 static std::atomic<uint64_t> g_launches{0};
 
 int fail(int code, const char* fmt, ...) {
@@ -207,7 +208,7 @@ constexpr size_t kGemmSemBytes = 16384;      // [n_tiles] tile semaphores ... [l
 
 // stream-K plan of the persistent kernel: the n_tiles*k_blocks work list is cut into runs of `per` k-blocks, one per CTA
 struct SkPlan {
-    int per, used, max_contrib;
+    int per, used, max_contrib, aligned;
 };
 int sk_max_contrib(int n_tiles, int k_blocks, int per) {
     int mc = 1;
@@ -218,27 +219,58 @@ int sk_max_contrib(int n_tiles, int k_blocks, int per) {
     }
     return mc;
 }
+// Default plan = UNIFORM split-K: the run length is the smallest divisor of k_blocks that still gives every CTA at most one
+// run (or whole tiles when there are more tiles than CTAs), so every CTA owns exactly one segment and the S = k_blocks / per
+// contributors of a tile (S a power of two) merge their partials together. B200_SK_STREAMK=1 selects ragged stream-K runs
+// (equal k-block counts per CTA, tiles finished by their lowest contributor) for experiments.
 SkPlan sk_plan(int n_tiles, int k_blocks, int grid, int bpad, size_t ws_partial_bytes) {
     const long total = (long)n_tiles * k_blocks;
-    int per = (int)((total + grid - 1) / grid);
+    const size_t slot = (size_t)bpad * kGemmTileN * sizeof(float);
+    int want = (int)((total + grid - 1) / grid);
+    SkPlan p{};
+    if (!env_int("B200_SK_STREAMK", 0)) {
+        int per = 0;
+        if (want >= k_blocks) {
+            per = (want + k_blocks - 1) / k_blocks * k_blocks;          // whole tiles, possibly several per CTA
+        } else {
+            for (int d = want; d <= k_blocks; ++d) {
+                const int S = k_blocks / d;
+                if (k_blocks % d == 0 && (S & (S - 1)) == 0 && S <= 16 && (size_t)n_tiles * S * slot <= ws_partial_bytes) {
+                    per = d;
+                    break;
+                }
+            }
+            if (!per) per = k_blocks;
+        }
+        p.per = per;
+        p.used = (int)((total + per - 1) / per);
+        p.max_contrib = per >= k_blocks ? 1 : k_blocks / per;
+        p.aligned = 1;
+        return p;
+    }
+    int per = want;
     const int min_run = env_int("B200_SK_MIN_RUN", 2);
     if (per < min_run) per = min_run < k_blocks ? min_run : k_blocks;
-    if (env_int("B200_SK_WHOLE_TILES", 0)) per = (per + k_blocks - 1) / k_blocks * k_blocks;
     int mc = sk_max_contrib(n_tiles, k_blocks, per);
-    const size_t slot = (size_t)bpad * kGemmTileN * sizeof(float);
     if (mc > 1 && (size_t)n_tiles * mc * slot > ws_partial_bytes) {
         per = (per + k_blocks - 1) / k_blocks * k_blocks;   // no room for partials: whole tiles per CTA (always valid)
         mc = 1;
     }
-    SkPlan p;
     p.per = per;
     p.used = (int)((total + per - 1) / per);
     p.max_contrib = mc;
+    p.aligned = 0;
     return p;
 }
 size_t sk_ws_bytes(int n_tiles, int k_blocks, int grid, int bpad) {
     SkPlan p = sk_plan(n_tiles, k_blocks, grid, bpad, (size_t)-1);
-    return p.max_contrib > 1 ? (size_t)n_tiles * p.max_contrib * bpad * kGemmTileN * sizeof(float) : 0;
+    size_t need = p.max_contrib > 1 ? (size_t)n_tiles * p.max_contrib * bpad * kGemmTileN * sizeof(float) : 0;
+    // the ragged stream-K plan (developer switch) never needs more than 3 + k_blocks / per slots per tile: cover it too
+    const long total = (long)n_tiles * k_blocks;
+    int per = (int)((total + grid - 1) / grid);
+    if (per < 2) per = 2;
+    const size_t ragged = (size_t)n_tiles * (size_t)(sk_max_contrib(n_tiles, k_blocks, per < k_blocks ? per : k_blocks)) * bpad * kGemmTileN * sizeof(float);
+    return need > ragged ? need : ragged;
 }
 
 }  // namespace
@@ -545,7 +577,7 @@ int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const
     ARG_CHECK(fmt != B200_FMT_INT8 || col_scale, "wo_gemm: INT8 needs col_scale");
     ARG_CHECK((((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) == 0, "wo_gemm: x / w / y must be 16-byte aligned");
     const int n_tiles = (N + kGemmTileN - 1) / kGemmTileN;
-    ARG_CHECK((size_t)n_tiles * sizeof(int) <= kGemmSemBytes - 64, "wo_gemm: N=%d too large", N);
+    ARG_CHECK(n_tiles <= 2032, "wo_gemm: N=%d too large", N);   // arrivals [0, 2048) + departures [2048, 4080) + 64 bytes of barrier words
     const int bpad = gemm_bpad(B);
     const bool silu_mul = (flags & B200_GEMM_SILU_MUL) != 0;
     ARG_CHECK(!silu_mul || N % 128 == 0, "wo_gemm: SILU_MUL needs N %% 128 == 0 (gate/up interleaved per 128-feature tile)");
@@ -560,8 +592,12 @@ int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const
         if (rc) return rc;
     }
 
-    // ---- weight-only INT8 / INT4 at decode batches: the persistent stream-K kernel (alone, or as one op of a program)
-    const bool streamk = fmt != B200_FMT_F16 && bpad <= 64 && !env_int("B200_GEMM_CLUSTERED", 0);
+    // ---- weight-only INT8 / INT4 at decode batches: inside a decode program the GEMM is an op of the persistent kernel
+    // (uniform split-K merged through L2). A stand-alone call uses the cluster kernel below (split-K merged through DSMEM):
+    // measured on B200 at B=32 (profiles/r02_gemm_paths.txt) the cluster kernel is faster for every Llama-3-8B shape;
+    // B200_GEMM_PERSISTENT=1 routes stand-alone calls through the persistent kernel too (experiments / tests).
+    const bool seg_capable = fmt != B200_FMT_F16 && bpad <= 64;
+    const bool streamk = seg_capable && (recording_fused(kOpGemm) || env_int("B200_GEMM_PERSISTENT", 0));
     if (streamk) {
         ARG_CHECK(workspace && workspace_bytes >= kGemmSemBytes, "wo_gemm: workspace of at least %zu bytes required", kGemmSemBytes);
         int grid = 0;
@@ -585,6 +621,7 @@ int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const
         g.total_kb = n_tiles * g.k_blocks;
         g.per_cta = plan.per;
         g.max_contrib = plan.max_contrib;
+        g.aligned = plan.aligned;
         g.sem = reinterpret_cast<int*>(workspace);
         g.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kGemmSemBytes);
         g.silu_mul = silu_mul ? 1 : 0;
@@ -923,8 +960,11 @@ int b200_program_launch(b200_program* p, void* stream) {
             rc = segment_grid(bf16, bpad, qfmt, &grid);
             if (rc) return rc;
             unsigned long long* tr = p->trace ? p->trace + (size_t)it.first * grid * 2 : nullptr;
+            // fine timeline (CTA 0): after the coarse region, [op][kFtSlots][kFtBlocks]
+            g_ftrace_next = p->trace ? p->trace + p->ops.size() * (size_t)grid * 2 + (size_t)it.first * kFtSlots * kFtBlocks : nullptr;
             rc = launch_segment(bf16, bpad, qfmt, nullptr, p->d_ops + it.first, it.count, p->d_bar + i * 64, grid, pdl, tr,
                                 (cudaStream_t)stream);
+            g_ftrace_next = nullptr;
         } else {
             rc = it.fn(stream);
         }

@@ -44,8 +44,10 @@ struct SkGemmParams {
     int total_kb;            // n_tiles * k_blocks
     int per_cta;             // k-blocks per CTA (stream-K run length)
     int max_contrib;         // upper bound of CTAs contributing to one tile (sizes the partial slots)
+    int aligned;             // 1: per_cta divides k_blocks -> every CTA owns exactly one segment and the S = k_blocks / per_cta
+                             //    contributors of a tile merge their partials TOGETHER (each reduces 1/S of the tile)
     float* ws;               // [n_tiles][max_contrib][bpad/4][128][4] fp32 partials
-    int* sem;                // [n_tiles] zero on entry / exit
+    int* sem;                // [n_tiles] arrivals, [2048 + n_tiles] departures; zero on entry / exit
     int silu_mul;            // 1: tile rows 2i / 2i+1 hold gate / up feature tile*64+i; y[b][tile*64+i] = silu(g)*u
 };
 
@@ -97,22 +99,48 @@ struct alignas(64) ProgOp {
 
 // ---- grid barrier: one monotonically increasing counter per launch; op i may touch dependent data once the counter has
 // reached i * gridDim.x (every CTA arrives exactly once per op).  The last CTA to leave the kernel resets it.
+// Spin-waits on global words poll with RELAXED loads and back off between polls (hundreds of threads hammering one L2
+// line with acquire loads starve the atomics they are waiting for -- and every other request to that L2 slice); one
+// acquire fence after the wait orders the following reads.
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// release-add without a return value: prior writes of this thread (and, by cumulativity, of the threads it has synchronised
+// with through a CTA barrier) are visible to whoever acquires the counter
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void spin_until_ge(const unsigned* p, unsigned target) {
+    unsigned spins = 0;
+    while (ld_relaxed_u32(p) < target) {
+        __nanosleep(32);
+        if (++spins > (1u << 22)) __trap();   // liveness guard (seconds): a lost arrival becomes an error, not a hung GPU
+    }
+    (void)ld_acquire_u32(p);                  // one acquire load orders the reads that follow (no full fence on this path)
+}
 __device__ __forceinline__ void grid_wait(const unsigned* bar, unsigned target) {
     if (target == 0) return;
-    unsigned spins = 0;
-    while (ld_acquire_u32(bar) < target) {
-        if (++spins > (1u << 23)) __trap();   // liveness guard (seconds): a lost arrival becomes an error, not a hung GPU
-    }
+    spin_until_ge(bar, target);
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tensormap_acquire(const CUtensorMap* m) {
     asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(m) : "memory");
 }
+
+// developer fine-grained timeline (CTA 0 only): ftrace[op][slot][block] = clock64; slots: 0 W issue, 1 X issue, 2 dq wfull seen
+// (warp 0), 3 dq aempty seen, 4 dq afull arrive, 5 MMA operands ready, 6 MMA issued, 7 epilogue begin/end
+constexpr int kFtSlots = 8, kFtBlocks = 48;
+#define B200_FT(ft, slot, it)                                                                                      \
+    do {                                                                                                           \
+        if ((ft) && blockIdx.x == 0 && (it) < kFtBlocks) (ft)[(slot) * kFtBlocks + (it)] = (unsigned long long)clock64(); \
+    } while (0)
 
 template <int FMT, int BPAD>
 struct SegCfg {
@@ -160,7 +188,7 @@ __device__ __forceinline__ void sk_range(const SkGemmParams& g, int cta, int& g0
 
 // ------------------------------------------------------------------------------------------------ role: weight producer
 template <int FMT, int BPAD>
-__device__ __forceinline__ void seg_w_producer(const ProgOp* op, const SegSmem<FMT, BPAD>& sm, uint32_t& cw) {
+__device__ __forceinline__ void seg_w_producer(const ProgOp* op, const SegSmem<FMT, BPAD>& sm, uint32_t& cw, unsigned long long* ft) {
     using C = SegCfg<FMT, BPAD>;
     int g0, g1;
     sk_range(op->g, blockIdx.x, g0, g1);
@@ -170,6 +198,7 @@ __device__ __forceinline__ void seg_w_producer(const ProgOp* op, const SegSmem<F
         for (int k = g0; k < g1; ++k, ++i, src += C::W_BYTES) {
             const uint32_t s = i % C::WS, ph = (i / C::WS) & 1;
             mbar_wait_a(sm.wempty(s), ph ^ 1);
+            B200_FT(ft, 0, k - g0);
             mbar_arrive_expect_tx_a(sm.wfull(s), C::W_BYTES);
             tma_bulk_load_a(sm.wring(s), src, C::W_BYTES, sm.wfull(s));
         }
@@ -181,7 +210,7 @@ __device__ __forceinline__ void seg_w_producer(const ProgOp* op, const SegSmem<F
 // ------------------------------------------------------------------------------------------------ role: activation producer
 template <int FMT, int BPAD>
 __device__ __forceinline__ void seg_x_producer(const ProgOp* op, const SegSmem<FMT, BPAD>& sm, uint32_t& cx, const unsigned* gbar,
-                                               unsigned target, bool from_gmem) {
+                                               unsigned target, bool from_gmem, unsigned long long* ft) {
     using C = SegCfg<FMT, BPAD>;
     int g0, g1;
     sk_range(op->g, blockIdx.x, g0, g1);
@@ -196,6 +225,7 @@ __device__ __forceinline__ void seg_x_producer(const ProgOp* op, const SegSmem<F
             const int k0 = (k % k_blocks) * kGemmBK;
             const uint32_t stage = sm.xring(s);
             mbar_wait_a(sm.xempty(s), ph ^ 1);
+            B200_FT(ft, 1, k - g0);
             mbar_arrive_expect_tx_a(sm.xfull(s), C::X_BYTES);
             tma_load_2d_a(stage, &op->xmap, k0, 0, sm.xfull(s));
             tma_load_2d_a(stage + BPAD * 128, &op->xmap, k0 + 64, 0, sm.xfull(s));
@@ -207,7 +237,7 @@ __device__ __forceinline__ void seg_x_producer(const ProgOp* op, const SegSmem<F
 
 // ------------------------------------------------------------------------------------------------ role: MMA issuer
 template <int FMT, typename T, int BPAD>
-__device__ __forceinline__ void seg_mma(const ProgOp* op, const SegSmem<FMT, BPAD>& sm, uint32_t tmem_base, uint32_t& cb, uint32_t& cs) {
+__device__ __forceinline__ void seg_mma(const ProgOp* op, const SegSmem<FMT, BPAD>& sm, uint32_t tmem_base, uint32_t& cb, uint32_t& cs, unsigned long long* ft) {
     using C = SegCfg<FMT, BPAD>;
     constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
     constexpr uint32_t IDESC = make_idesc_f16(kGemmTileN, BPAD, kBf16);
@@ -229,6 +259,7 @@ __device__ __forceinline__ void seg_mma(const ProgOp* op, const SegSmem<FMT, BPA
             mbar_wait_a(sm.afull(a), pha);
             tc_fence_after();
             if (elect_one()) {
+                B200_FT(ft, 5, kk - g0);
                 const uint32_t xs = sm.xring(sx);
 #pragma unroll
                 for (int j = 0; j < kGemmBK / 16; ++j) {
@@ -238,6 +269,7 @@ __device__ __forceinline__ void seg_mma(const ProgOp* op, const SegSmem<FMT, BPA
                 umma_commit_a(sm.xempty(sx));
                 umma_commit_a(sm.aempty(a));
                 if (kk == e - 1) umma_commit_a(sm.dfull());
+                B200_FT(ft, 6, kk - g0);
             }
             __syncwarp();
         }
@@ -252,7 +284,7 @@ template <typename T>
 __device__ __forceinline__ float silu_mul_f(float g, float u) { return g / (1.f + __expf(-g)) * u; }
 
 template <int FMT, typename T, int BPAD>
-__device__ __forceinline__ void seg_dq(const ProgOp* op, const SegSmem<FMT, BPAD>& sm, uint32_t tmem_base, uint32_t& cb, uint32_t& cs) {
+__device__ __forceinline__ void seg_dq(const ProgOp* op, const SegSmem<FMT, BPAD>& sm, uint32_t tmem_base, uint32_t& cb, uint32_t& cs, unsigned long long* ft) {
     using C = SegCfg<FMT, BPAD>;
     const SkGemmParams g = op->g;      // by value: the fields live in registers, not behind a global load per use
     int g0, g1;
@@ -277,6 +309,7 @@ __device__ __forceinline__ void seg_dq(const ProgOp* op, const SegSmem<FMT, BPAD
             const uint32_t s = i % C::WS, ph = (i / C::WS) & 1;
             const uint32_t a = i % kSegAStages, pha = (i / kSegAStages) & 1;
             mbar_wait_a(sm.wfull(s), ph);
+            if ((threadIdx.x & 127) == 0) B200_FT(ft, 2, kk - g0);
             const uint32_t wb = sm.wring(s);
             typename Pair<T>::type s2, zs2;
             if (FMT == kFmtInt4) {
@@ -323,6 +356,7 @@ __device__ __forceinline__ void seg_dq(const ProgOp* op, const SegSmem<FMT, BPAD
                 }
                 if (half == 0) {
                     mbar_wait_a(sm.aempty(a), pha ^ 1);
+                    if ((threadIdx.x & 127) == 0) B200_FT(ft, 3, kk - g0);
                     tc_fence_after();
                 }
                 const uint32_t dst = tmem_a + lane_addr + a * 64 + half * 32;
@@ -333,6 +367,7 @@ __device__ __forceinline__ void seg_dq(const ProgOp* op, const SegSmem<FMT, BPAD
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_a(sm.afull(a));
+            if ((threadIdx.x & 127) == 0) B200_FT(ft, 4, kk - g0);
         }
 
         // ---- epilogue of the segment [k, e) of `tile`
@@ -361,8 +396,94 @@ __device__ __forceinline__ void seg_dq(const ProgOp* op, const SegSmem<FMT, BPAD
                 }
             }
         };
+        if (threadIdx.x == 0) B200_FT(ft, 7, 2 * (int)(cs & 7));
         mbar_wait_a(sm.dfull(), cs & 1);
         tc_fence_after();
+        if (threadIdx.x == 0) B200_FT(ft, 7, 2 * (int)(cs & 7) + 1);
+        if (g.aligned && nact > 1) {
+            // ---- uniform split-K (every CTA of this op owns exactly one segment): the S contributors of the tile publish
+            // their fp32 partials to L2, wait for each other, and EACH reduces 1/S of the tile in fixed order 0..S-1
+            // (deterministic) -- S float4 loads in flight per thread, one round trip, instead of one CTA loading S partials.
+            constexpr int ITEMS = (BPAD / 4) * kGemmTileN;       // (4 batch columns) x (feature row) units of the tile
+            constexpr size_t SLOT4 = (size_t)ITEMS;
+            float4* part0 = reinterpret_cast<float4*>(g.ws) + (size_t)tile * g.max_contrib * SLOT4;
+            for (int sl = grp; sl < SLICES; sl += 2) {
+                uint32_t r[16];
+                tmem_ld_32x32b_x16(tmem_d + lane_addr + sl * 16, r);
+                tmem_wait_ld();
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    __stcg(&part0[(size_t)my_idx * SLOT4 + (size_t)(sl * 4 + q) * kGemmTileN + row],
+                           make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                       __uint_as_float(r[4 * q + 3])));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(sm.dempty());
+            asm volatile("bar.sync 1, %0;" ::"n"(kSegDqThreads) : "memory");
+            unsigned* arrivals = reinterpret_cast<unsigned*>(g.sem) + tile;
+            if (threadIdx.x == 0) red_release_add(arrivals, 1u);
+            if (lane == 0) spin_until_ge(arrivals, (unsigned)nact);
+            __syncwarp();
+            if (threadIdx.x == 0) B200_FT(ft, 7, 24 + (int)(cs & 7));
+            const int per_items = (ITEMS + nact - 1) / nact;
+            const int it0 = my_idx * per_items, it1 = min(ITEMS, it0 + per_items);
+            for (int base = it0 + (int)(threadIdx.x & ~31u); base < it1; base += kSegDqThreads) {   // warp-uniform trip count
+                const int item = base + lane;
+                const bool ok = item < it1;
+                const int q = item / kGemmTileN, rrow = item % kGemmTileN;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) {
+                    float4 t[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        t[c] = c < nact ? __ldcg(&part0[(size_t)c * SLOT4 + (size_t)q * kGemmTileN + rrow]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        acc.x += t[c].x;
+                        acc.y += t[c].y;
+                        acc.z += t[c].z;
+                        acc.w += t[c].w;
+                    }
+                    for (int c = 8; c < nact; ++c) {
+                        const float4 u = __ldcg(&part0[(size_t)c * SLOT4 + (size_t)q * kGemmTileN + rrow]);
+                        acc.x += u.x;
+                        acc.y += u.y;
+                        acc.z += u.z;
+                        acc.w += u.w;
+                    }
+                }
+                // feature `rrow` of the tile, batch columns 4q .. 4q+3
+                const int nn = tile * kGemmTileN + rrow;
+                float cs2 = 1.f, bi2 = 0.f;
+                if (ok && nn < g.N) {
+                    if (FMT == kFmtInt8) cs2 = to_f32<T>(reinterpret_cast<const T*>(g.col_scale)[nn]);
+                    if (g.bias) bi2 = to_f32<T>(reinterpret_cast<const T*>(g.bias)[nn]);
+                }
+                const float vals[4] = {fmaf(acc.x, cs2, bi2), fmaf(acc.y, cs2, bi2), fmaf(acc.z, cs2, bi2), fmaf(acc.w, cs2, bi2)};
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4) {
+                    const int b = q * 4 + e4;
+                    if (g.silu_mul) {
+                        const float other = __shfl_xor_sync(0xffffffffu, vals[e4], 1);
+                        const int f = tile * 64 + (rrow >> 1);
+                        if (ok && !(rrow & 1) && b < g.B && f < g.N / 2)
+                            yp[(size_t)b * (g.N / 2) + f] = from_f32<T>(silu_mul_f<T>(vals[e4], other));
+                    } else if (ok && nn < g.N && b < g.B) {
+                        yp[(size_t)b * g.N + nn] = from_f32<T>(vals[e4]);
+                    }
+                }
+            }
+            // the last contributor to leave resets the tile's counters for the next op / launch
+            asm volatile("bar.sync 1, %0;" ::"n"(kSegDqThreads) : "memory");
+            if (threadIdx.x == 0) {
+                unsigned* departures = reinterpret_cast<unsigned*>(g.sem) + 2048 + tile;
+                if (atomicAdd(departures, 1u) == (unsigned)(nact - 1)) {
+                    *arrivals = 0;
+                    *departures = 0;
+                }
+            }
+        } else {
         // Stream-K fix-up with a DESIGNATED reducer: contributor 0 (the lowest CTA; the tile is the LAST segment of its run, so
         // it finishes the tile last in time) keeps its partial in registers, waits until the other contributors have
         // published theirs, adds them in fixed order 1..nact-1 (deterministic) and stores the result. The others store
@@ -372,11 +493,7 @@ __device__ __forceinline__ void seg_dq(const ProgOp* op, const SegSmem<FMT, BPAD
         float4* part0 = reinterpret_cast<float4*>(g.ws) + (size_t)tile * g.max_contrib * SLOT4;
         if (nact > 1 && my_idx == 0) {
             // wait for the nact-1 published partials (lane 0 of every warp polls; no CTA barrier on this path)
-            if (lane == 0) {
-                unsigned spins = 0;
-                while (ld_acquire_u32(reinterpret_cast<const unsigned*>(g.sem) + tile) < (unsigned)(nact - 1))
-                    if (++spins > (1u << 23)) __trap();
-            }
+            if (lane == 0) spin_until_ge(reinterpret_cast<const unsigned*>(g.sem) + tile, (unsigned)(nact - 1));
             __syncwarp();
         }
         for (int sl = grp; sl < SLICES; sl += 2) {
@@ -425,6 +542,8 @@ __device__ __forceinline__ void seg_dq(const ProgOp* op, const SegSmem<FMT, BPAD
                 }
             }
         }
+        }
+        if (threadIdx.x == 0) B200_FT(ft, 7, 16 + (int)(cs & 7));
         ++cs;
         k = e;
     }
@@ -562,7 +681,7 @@ __device__ __forceinline__ void seg_block_table(const BlockTableParams& p, int c
 template <typename T, int BPAD, int QFMT>
 __global__ void __launch_bounds__(kSegThreads, 2)
 decode_segment_kernel(const __grid_constant__ ProgOp op0, const ProgOp* __restrict__ ops, int nops, unsigned* gbar, int use_pdl,
-                      unsigned long long* trace) {
+                      unsigned long long* trace, unsigned long long* ftrace) {
     using C = SegCfg<QFMT, BPAD>;
     extern __shared__ __align__(1024) uint8_t smem[];
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
@@ -603,7 +722,7 @@ decode_segment_kernel(const __grid_constant__ ProgOp op0, const ProgOp* __restri
         uint32_t cw = 0;
         for (int i = 0; i < nops; ++i) {
             const ProgOp* op = ops ? &ops[i] : &op0;
-            if (op->type == kOpGemm) seg_w_producer<QFMT, BPAD>(op, sm, cw);
+            if (op->type == kOpGemm) seg_w_producer<QFMT, BPAD>(op, sm, cw, ftrace ? ftrace + (size_t)i * kFtSlots * kFtBlocks : nullptr);
         }
     } else if (warp == kSegDqWarps + 1) {
         // ---- activation producer
@@ -611,14 +730,14 @@ decode_segment_kernel(const __grid_constant__ ProgOp op0, const ProgOp* __restri
         uint32_t cx = 0;
         for (int i = 0; i < nops; ++i) {
             const ProgOp* op = ops ? &ops[i] : &op0;
-            if (op->type == kOpGemm) seg_x_producer<QFMT, BPAD>(op, sm, cx, gbar, (unsigned)i * G, ops != nullptr);
+            if (op->type == kOpGemm) seg_x_producer<QFMT, BPAD>(op, sm, cx, gbar, (unsigned)i * G, ops != nullptr, ftrace ? ftrace + (size_t)i * kFtSlots * kFtBlocks : nullptr);
         }
     } else if (warp == kSegDqWarps + 2) {
         // ---- MMA issuer
         uint32_t cb = 0, cs = 0;
         for (int i = 0; i < nops; ++i) {
             const ProgOp* op = ops ? &ops[i] : &op0;
-            if (op->type == kOpGemm) seg_mma<QFMT, T, BPAD>(op, sm, tmem_base, cb, cs);
+            if (op->type == kOpGemm) seg_mma<QFMT, T, BPAD>(op, sm, tmem_base, cb, cs, ftrace ? ftrace + (size_t)i * kFtSlots * kFtBlocks : nullptr);
         }
     } else {
         // ---- dequant / epilogue / glue warps: the role that owns the grid barrier
@@ -632,13 +751,10 @@ decode_segment_kernel(const __grid_constant__ ProgOp op0, const ProgOp* __restri
                 trace[((size_t)i * G + blockIdx.x) * 2 + 0] = gt;
             }
             if (op->type == kOpGemm) {
-                seg_dq<QFMT, T, BPAD>(op, sm, tmem_base, cb, cs);
+                seg_dq<QFMT, T, BPAD>(op, sm, tmem_base, cb, cs, ftrace ? ftrace + (size_t)i * kFtSlots * kFtBlocks : nullptr);
             } else {
                 // glue ops read what the previous op wrote: wait for it (thread 0 polls, the named barrier publishes)
-                if (threadIdx.x == 0) {
-                    grid_wait(gbar, (unsigned)i * G);
-                    __threadfence();
-                }
+                if (threadIdx.x == 0) grid_wait(gbar, (unsigned)i * G);
                 asm volatile("bar.sync 1, %0;" ::"n"(kSegDqThreads) : "memory");
                 if (op->type == kOpNorm) seg_norm<T>(op->n, sm, blockIdx.x, G);
                 else if (op->type == kOpRope) seg_rope<T>(op->r, blockIdx.x, G);
@@ -659,8 +775,7 @@ decode_segment_kernel(const __grid_constant__ ProgOp op0, const ProgOp* __restri
                 // ops i-1, i would run ahead and their early arrivals could push the counter past i*G while others still
                 // compute op i-1. (Glue ops and the activation producer have waited already; this is for idle / GEMM paths.)
                 grid_wait(gbar, (unsigned)i * G);
-                __threadfence();
-                atomicAdd(gbar, 1u);
+                red_release_add(gbar, 1u);
             }
         }
         tc_fence_before();

@@ -21,6 +21,7 @@ int fail(int code, const char* fmt, ...);
 int launched(const char* what);
 int env_int(const char* name, int dflt);
 int num_sms();
+extern thread_local unsigned long long* g_ftrace_next;   // developer: fine timeline buffer of the next segment launch
 
 #define ARG_CHECK(cond, ...)                                           \
     do {                                                               \

@@ -11,6 +11,7 @@ namespace {
 template <typename T, int BPAD, int QFMT>
 int seg_one(const ProgOp* op0, const ProgOp* d_ops, int nops, unsigned* gbar, int grid, bool pdl, unsigned long long* trace,
             cudaStream_t st, int* grid_out) {
+    unsigned long long* ftrace = g_ftrace_next;   // developer fine timeline of the next launch (b200_program_set_trace)
     auto kern = decode_segment_kernel<T, BPAD, QFMT>;
     constexpr int smem = SegCfg<QFMT, BPAD>::SMEM;
     static bool configured[16] = {};
@@ -20,11 +21,20 @@ int seg_one(const ProgOp* op0, const ProgOp* d_ops, int nops, unsigned* gbar, in
     if (dev < 0 || dev >= 16) return fail(B200_EINVAL, "device ordinal %d out of range", dev);
     if (!configured[dev]) {
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        // two ~104 KB CTAs per SM need the full shared-memory carve-out; without the preference the occupancy query
+        // (and the co-resident grid derived from it) reports one CTA per SM
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         int occ = 0, sms = 0;
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSegThreads, smem));
         CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         if (occ < 1) return fail(B200_ECUDA, "decode_segment_kernel does not fit on an SM (smem %d)", smem);
-        max_grid[dev] = (occ > 2 ? 2 : occ) * sms;      // every CTA must be co-resident: the ops synchronise grid-wide
+        // Every CTA must be co-resident (the ops synchronise grid-wide). Two CTAs per SM fit by construction (__launch_bounds__(352, 2),
+        // 2 x (SMEM + 1 KB) <= 227 KB, 2 x 256 TMEM columns); measured on B200: 296 CTAs run concurrently although the occupancy
+        // query answers 1 for this kernel. A wrong assumption here cannot hang the GPU: every spin-wait traps after a bound.
+        static_assert(2 * (smem + 1024) <= 227 * 1024, "two CTAs per SM must fit");
+        max_grid[dev] = 2 * sms;
+        if (env_int("B200_SEG_GRID", 0) > 0) max_grid[dev] = env_int("B200_SEG_GRID", 0);   // developer override
+        if (env_int("B200_DEBUG", 0)) fprintf(stderr, "[b200] decode_segment_kernel<bpad %d, fmt %d>: occupancy %d CTAs/SM, grid %d\n", BPAD, QFMT, occ, max_grid[dev]);
         configured[dev] = true;
     }
     if (grid_out) *grid_out = max_grid[dev];
@@ -41,7 +51,7 @@ int seg_one(const ProgOp* op0, const ProgOp* d_ops, int nops, unsigned* gbar, in
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     static const ProgOp dummy{};
-    CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, op0 ? *op0 : dummy, d_ops, nops, gbar, pdl ? 1 : 0, trace));
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, op0 ? *op0 : dummy, d_ops, nops, gbar, pdl ? 1 : 0, trace, ftrace));
     return launched("decode_segment_kernel");
 }
 

@@ -1,6 +1,7 @@
 """GPU parity tests (run by the driver with -m gpu on a B200). Everything goes through the C ABI
 (rtp_llm_b200.ops -> libb200_decode.so) and is compared with the CPU oracle on the same seeded inputs, with the golden
-fixtures the reference's code produced, and -- at BASELINE.json's full sizes -- with a deliberately naive GPU kernel."""
+fixtures the reference's code produced -- at BASELINE.json's full sizes too (the OpenMP oracle finishes those in well under
+a second per case); a deliberately naive GPU kernel (test-only library) is kept as a second opinion."""
 import os
 
 import numpy as np
@@ -70,7 +71,7 @@ def test_attention_vs_oracle(case):
 @pytest.mark.parametrize("cfg", [("Llama-3-8B B32 S2048", 32, 32, 8, 64, 2048, False),
                                  ("Llama-3-8B B32 S2048 ragged", 32, 32, 8, 64, 2048, True),
                                  ("Qwen2-72B TP8 B16 S8192", 16, 8, 1, 64, 8192, False)], ids=lambda c: c[0])
-def test_attention_full_size_vs_naive_gpu_kernel(cfg):
+def test_attention_full_size_vs_oracle(cfg):
     name, B, Hq, Hkv, T, S, ragged = cfg
     _run(probe.attn_vs_ref_big, name, B, Hq, Hkv, T, S, torch.float16, ragged)
 
@@ -100,9 +101,33 @@ def test_gemm_vs_oracle(fmt, case):
                                  ("int4 Llama w13 B64", B200_FMT_INT4, 64, 4096, 28672),
                                  ("int8 Llama o B32", B200_FMT_INT8, 32, 4096, 4096),
                                  ("f16 lm_head slice B32", B200_FMT_F16, 32, 4096, 16032)], ids=lambda c: c[0])
-def test_gemm_full_size_vs_naive_gpu_kernel(cfg):
+def test_gemm_full_size_vs_oracle(cfg):
+    """BASELINE shapes: checked against the CPU oracle (and, as a second opinion, the naive GPU kernel)."""
     name, fmt, B, K, N = cfg
     _run(probe.gemm_case, name, fmt, B, K, N, big=True)
+
+
+PERSISTENT = [
+    ("uniform split", B200_FMT_INT4, 32, 1024, 256, {}),
+    ("uniform split bias int8", B200_FMT_INT8, 19, 1024, 384, dict(bias=True)),
+    ("whole tiles bf16", B200_FMT_INT4, 8, 256, 256, dict(dtype=torch.bfloat16)),
+    ("ragged N bpad64", B200_FMT_INT4, 33, 512, 200, {}),
+    ("Llama w2 B32", B200_FMT_INT4, 32, 14336, 4096, dict(big=True)),
+    ("ragged stream-K Llama w13 B32", B200_FMT_INT4, 32, 4096, 28672, dict(big=True, env_extra={"B200_SK_STREAMK": 1})),
+    ("ragged stream-K small", B200_FMT_INT8, 16, 1024, 640, dict(env_extra={"B200_SK_STREAMK": 1})),
+]
+
+
+@pytest.mark.parametrize("case", PERSISTENT, ids=[c[0] for c in PERSISTENT])
+def test_gemm_persistent_kernel_standalone(case):
+    """The persistent kernel of the decode programs (csrc/decode_program.cuh) run as a one-op program: uniform split-K
+    merged by all contributors, whole tiles, and the ragged stream-K plan with a designated reducer."""
+    name, fmt, B, K, N, kw = case
+    kw = dict(kw)
+    env = {"B200_GEMM_PERSISTENT": 1}
+    env.update(kw.pop("env_extra", {}))
+    _run(probe.gemm_case, name, fmt, B, K, N, env=env, **kw)
+    _run(probe.gemm_silu_case, name + " silu", fmt, 7, 512, 192, env=env)
 
 
 @pytest.mark.parametrize("fmt", [B200_FMT_F16, B200_FMT_INT8, B200_FMT_INT4], ids=["f16", "int8", "int4"])
