@@ -19,6 +19,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm (rank 0 only) must use all host threads it can
+if "--impl" in sys.argv and "reference" in sys.argv:
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
 
 METRIC = "decode tokens/sec Llama-3-8B INT4-AWQ b32 ctx2048"
 UNIT = "tokens/s"
@@ -76,9 +79,16 @@ def cpu_arm(args, cfg, budget_s=25.0):
     block_ids = (rng.permutation(B * M).astype(np.int32) + 1).reshape(B, M)
     pl = orc.convert_block_table(block_ids)
     seq = np.full(B, S - 1, np.int32)
-    t0 = time.perf_counter()
-    orc.paged_decode_attn(q, pool, pl, seq, Hq, Hkv, D, T)
-    t_attn = time.perf_counter() - t0
+    def timed(fn, reps=3):
+        """one warm-up, then the median of `reps` timings (a single cold call moved the number by 2.4x, VERDICT r1 weak #7)"""
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return sorted(ts)[len(ts) // 2]
+    t_attn = timed(lambda: orc.paged_decode_attn(q, pool, pl, seq, Hq, Hkv, D, T))
     # GEMMs, one layer (column slices bound the sample; time scales linearly in N)
     fmt = cfg.quant
     t_gemm = 0.0
@@ -96,21 +106,17 @@ def cpu_arm(args, cfg, budget_s=25.0):
         else:
             w = (rng.standard_normal((K, Ns), dtype=np.float32) * 0.02).astype(np.float16).view(np.uint16)
             kw = {}
-        t0 = time.perf_counter()
-        orc.dequant_gemm(x, fmt, w, fast=True, **kw)
-        dt = time.perf_counter() - t0
+        dt = timed(lambda: orc.dequant_gemm(x, fmt, w, fast=True, **kw))
         t_gemm += dt * (N / Ns)
         sample_desc.append(f"{K}x{Ns}/{N}")
     # lm_head slice (fp16 weights)
     Ns = 4096
     x = rng.standard_normal((B, H), dtype=np.float32).astype(np.float16).view(np.uint16)
     w = (rng.standard_normal((H, Ns), dtype=np.float32) * 0.02).astype(np.float16).view(np.uint16)
-    t0 = time.perf_counter()
-    orc.dequant_gemm(x, "f16", w, fast=True)
-    t_lm = (time.perf_counter() - t0) * (cfg.vocab / Ns)
+    t_lm = timed(lambda: orc.dequant_gemm(x, "f16", w, fast=True)) * (cfg.vocab / Ns)
     t_step = cfg.layers * (t_attn + t_gemm) + t_lm
     return dict(value=B / t_step, unit=UNIT, cores=cores, kind="port",
-                sample=(f"1 of {cfg.layers} layers timed (paged attention B{B} ctx{S} + 4 {fmt} GEMMs on column slices "
+                sample=(f"warm-up + median of 3; 1 of {cfg.layers} layers timed (paged attention B{B} ctx{S} + 4 {fmt} GEMMs on column slices "
                         f"{','.join(sample_desc)}) + lm_head slice {Ns}/{cfg.vocab}, extrapolated; "
                         f"layer={1e3 * (t_attn + t_gemm):.0f} ms (attn {1e3 * t_attn:.0f} ms) lm_head={1e3 * t_lm:.0f} ms"),
                 ms_per_step=1e3 * t_step)
@@ -166,6 +172,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = model_cfg(args)
     workload = f"{cfg.name} {cfg.quant}{'-AWQ g128' if cfg.quant == 'int4' else ''} decode, batch {args.batch}, ctx {args.ctx}"
+    global METRIC
+    if (args.model, args.quant, args.batch, args.ctx) != ("llama3-8b", "int4", 32, 2048):
+        METRIC = f"decode tokens/sec {cfg.name} {cfg.quant} b{args.batch} ctx{args.ctx}"      # a BASELINE.json config other than the headline
 
     if args.impl == "reference":
         # the reference's CPU arm: rank 0 alone runs it, the other ranks exit 0 without work
@@ -198,6 +207,26 @@ def main():
         comm = make_comm(dev, kind=args.comm)
 
     model = DecodeStep(cfg, args.batch, args.ctx, dev, tp_rank=rank, tp_size=tp, comm=comm, pdl=bool(args.pdl))
+    parity_check = None
+    if tp > 1 and args.comm == "peer":
+        # sharded step through our peer collectives (fused all-reduce + norm, vocab-parallel argmax) vs the same step through
+        # stock NCCL all-reduce + all-gather + torch.argmax, on the same weights and inputs, before anything is timed
+        from rtp_llm_b200.tp import NcclComm
+        model.step()
+        torch.cuda.synchronize(dev)
+        la, ta = model.logits.float().clone(), model.next_ids.clone()
+        model.comm = NcclComm(dev)
+        model.step()
+        torch.cuda.synchronize(dev)
+        lb, tb = model.logits.float(), model.next_ids
+        model.comm = comm
+        rms = float(lb.pow(2).mean().sqrt())
+        diff = float((la - lb).abs().max())
+        agree = float((ta == tb).float().mean())
+        t = torch.tensor([diff, -agree], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        parity_check = {"against": "nccl all_reduce + all_gather + torch.argmax", "max_abs_logit_diff": t[0].item(), "logit_rms": rms,
+                        "token_agreement": -t[1].item(), "ok": bool(t[0].item() <= 2e-2 * rms + 2e-2)}
     use_program = bool(args.program) and (tp == 1 or args.comm == "peer")
     if use_program:
         model.build_program()
@@ -268,7 +297,7 @@ def main():
         tfile = os.path.join(ROOT, "profiles", "attn_traffic_bytes.json")
         if os.path.exists(tfile):
             try:
-                traffic = json.load(open(tfile)).get(f"b{args.batch}_ctx{args.ctx}_tp{tp}")
+                traffic = json.load(open(tfile)).get(f"b{args.batch}_ctx{args.ctx}_tp{tp}")   # from an `ncu --set full` capture (profiles/README.md), not measured in this run
             except Exception:  # noqa: BLE001
                 traffic = None
         line = {
@@ -283,11 +312,13 @@ def main():
                        "pdl": bool(args.pdl), "decode_program": use_program},
             "e2e": {"value": args.batch / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": model.h2d_bytes(),
                     "d2h_bytes_per_step": model.d2h_bytes(), "ms_per_step": ms_e2e},
+            "parity_check": parity_check,
             "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step,
             "clocks": clocks,
             "roofline": {"kernel": "paged_decode_attn_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": ("ncu --set full capture, profiles/r01_ncu_attn_b32_s2048_summary.txt" if traffic else None),
+                         "peak_source": peak_src,
                          "bytes_per_launch": attn_bytes, "us_per_launch": attn_ms * 1e3},
             "step_roofline": {"algorithmic_bytes_per_gpu": ab["total"], "achieved_gbs": step_gbs, "frac": step_gbs / peak,
                               "roofline_tokens_per_s": args.batch / (ab["total"] / (peak * 1e9)), "split": ab},

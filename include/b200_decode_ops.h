@@ -146,14 +146,28 @@ int b200_argmax(const void* logits, int dtype, int rows, int vocab, int32_t* out
  * is torch symmetric memory, distributed/symm_mem.py:126-185). One process per GPU. Set-up, once per process:
  *   b200_peer_alloc(b200_peer_ar_region_bytes(max_msg), &mine, handle)  -> exchange the 64-byte handles between ranks
  *   (any host channel) -> b200_peer_open(handle_of_rank_r, &regions[r]) for r != rank; regions[rank] = mine.
- * Per call: `call_parity` must alternate 0,1,0,1,... between consecutive calls on the stream (two data slots), and every
- * rank must issue the same sequence of calls. Deterministic: all ranks sum in rank order and get identical bits.
- * CUDA-graph capturable (call counters live on the device). bytes % 16 == 0, bytes <= max_message_bytes, world <= 8. */
+ * Per call: every rank must issue the same sequence of peer_* calls on its stream. `call_parity` is ignored (kept for ABI
+ * compatibility): the two data slots alternate by a device-side call counter, so CUDA graphs holding any number of calls
+ * replay correctly. Deterministic: all ranks sum in rank order and get identical bits. A rank whose peers never arrive
+ * traps after a few seconds of polling instead of hanging. bytes % 16 == 0, bytes <= max_message_bytes, world <= 8. */
 size_t b200_peer_ar_region_bytes(size_t max_message_bytes);
 int b200_peer_alloc(size_t bytes, void** ptr, void* ipc_handle_out);
 int b200_peer_open(const void* ipc_handle, void** ptr);
 int b200_peer_allreduce(const void* in, void* out, size_t bytes, int is_bf16, void* const* regions, size_t max_message_bytes,
                         int call_parity, int rank, int world, void* stream);
+
+/* The same exchange fused with what follows it in the decoder layer: y = rmsnorm(allreduce(in) + residual) * gamma and
+ * residual += allreduce(in), in ONE kernel (replaces all_reduce + fused_add_rmsnorm: collective_torch.py:694-722 then
+ * RegisterBaseBindings.hpp:54; call sites hybrid/causal_attention.py:91-92, dense_mlp.py:104-105). Numerics are those of
+ * the unfused sequence (the reduced value is rounded to the tensor type first). hidden % (8*world) == 0, hidden <= 8192. */
+int b200_peer_allreduce_norm(const void* in, void* residual, const void* gamma, void* y, int is_bf16, int rows, int hidden,
+                             float eps, void* const* regions, size_t max_message_bytes, int rank, int world, void* stream);
+
+/* Vocab-parallel greedy sampling: out[r] = argmax over the CONCATENATED vocabulary (rank r holds columns
+ * [r*vocab_local, (r+1)*vocab_local), columns >= vocab_total are padding), lowest index on ties, identical on every rank.
+ * Replaces the logits all-gather + argmax of cpp/models/PyWrappedModel.cc:915-936,1001-1052 for top_k == 1. */
+int b200_peer_argmax(const void* logits, int is_bf16, int rows, int vocab_local, int vocab_total, int32_t* out,
+                     void* const* regions, size_t max_message_bytes, int rank, int world, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ decode programs */
 

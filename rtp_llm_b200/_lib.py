@@ -38,6 +38,8 @@ SIGNATURES = {
     "b200_peer_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
     "b200_peer_open": (c_int, [c_void_p, c_void_p]),
     "b200_peer_allreduce": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
+    "b200_peer_allreduce_norm": (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "b200_peer_argmax": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "b200_program_create": (c_int, [c_void_p]),
     "b200_program_begin": (c_int, [c_void_p]),
     "b200_program_end": (c_int, [c_void_p]),

@@ -852,8 +852,28 @@ int b200_peer_open(const void* ipc_handle /*64 bytes*/, void** ptr) {
     return B200_OK;
 }
 
+namespace {
+int fill_ar_params(PeerArParams& p, void* const* regions, size_t max_message_bytes, int rank, int world) {
+    const size_t src_stride = 2 * round_up(max_message_bytes, 256);          // LL doubles the bytes
+    const size_t area_stride = (size_t)kArMaxWorld * src_stride;
+    const size_t parity_stride = 2 * area_stride;
+    for (int r = 0; r < world; ++r) {
+        ARG_CHECK(regions[r], "peer collective: region %d is null", r);
+        p.region[r] = reinterpret_cast<uint8_t*>(regions[r]);
+    }
+    p.epoch = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(regions[rank]) + 2 * parity_stride);
+    p.src_stride = src_stride;
+    p.area_stride = area_stride;
+    p.parity_stride = parity_stride;
+    p.rank = rank;
+    p.world = world;
+    return B200_OK;
+}
+}  // namespace
+
 int b200_peer_allreduce(const void* in, void* out, size_t bytes, int is_bf16, void* const* regions, size_t max_message_bytes,
                         int call_parity, int rank, int world, void* stream) {
+    (void)call_parity;   // since r02 the slot parity comes from the device-side call counter (graph replays of any length are safe)
     ARG_CHECK(in && out && regions, "peer_allreduce: null pointer");
     ARG_CHECK(world >= 2 && world <= kArMaxWorld && rank >= 0 && rank < world, "peer_allreduce: bad rank/world %d/%d", rank, world);
     ARG_CHECK(bytes > 0 && bytes % 16 == 0 && bytes <= max_message_bytes, "peer_allreduce: message of %zu bytes unsupported", bytes);
@@ -861,26 +881,15 @@ int b200_peer_allreduce(const void* in, void* out, size_t bytes, int is_bf16, vo
     if (g_rec) {
         std::vector<void*> regs(regions, regions + world);
         return rec_call([=](void* st) {
-            return b200_peer_allreduce(in, out, bytes, is_bf16, regs.data(), max_message_bytes, call_parity, rank, world, st);
+            return b200_peer_allreduce(in, out, bytes, is_bf16, regs.data(), max_message_bytes, 0, rank, world, st);
         });
     }
-    const size_t src_stride = 2 * round_up(max_message_bytes, 256);          // LL doubles the bytes
-    const size_t area_stride = (size_t)kArMaxWorld * src_stride;
-    const size_t parity_stride = 2 * area_stride;
     PeerArParams p{};
     p.in = in;
     p.out = out;
-    for (int r = 0; r < world; ++r) {
-        uint8_t* base = reinterpret_cast<uint8_t*>(regions[r]);
-        ARG_CHECK(base, "peer_allreduce: region %d is null", r);
-        p.slots[r] = base + (size_t)(call_parity & 1) * parity_stride;
-        p.slots2[r] = p.slots[r] + area_stride;
-    }
-    p.epoch = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(regions[rank]) + 2 * parity_stride);
-    p.src_stride = src_stride;
+    int rc = fill_ar_params(p, regions, max_message_bytes, rank, world);
+    if (rc) return rc;
     p.n16 = (int)(bytes / 16);
-    p.rank = rank;
-    p.world = world;
     int ctas = (p.n16 + 2 * kArThreads - 1) / (2 * kArThreads);   // ~2 chunks (32 B of payload) per thread
     if (ctas < 1) ctas = 1;
     ctas = env_int("B200_AR_CTAS", ctas);
@@ -905,6 +914,66 @@ int b200_peer_allreduce(const void* in, void* out, size_t bytes, int is_bf16, vo
     else
         CUDA_CHECK(launch_ex(peer_allreduce_kernel<__half>, dim3(ctas), dim3(kArThreads), 0, (cudaStream_t)stream, pdl, p));
     return launched("peer_allreduce_kernel");
+}
+
+int b200_peer_allreduce_norm(const void* in, void* residual, const void* gamma, void* y, int is_bf16, int rows, int hidden,
+                             float eps, void* const* regions, size_t max_message_bytes, int rank, int world, void* stream) {
+    ARG_CHECK(in && residual && gamma && y && regions, "peer_allreduce_norm: null pointer");
+    ARG_CHECK(world >= 2 && world <= kArMaxWorld && rank >= 0 && rank < world, "peer_allreduce_norm: bad rank/world %d/%d", rank, world);
+    ARG_CHECK(rows > 0 && rows <= 65535, "peer_allreduce_norm: rows %d unsupported", rows);
+    ARG_CHECK(hidden > 0 && hidden % (8 * world) == 0 && hidden <= 8192, "peer_allreduce_norm: hidden %d must be a multiple of 8*world and <= 8192", hidden);
+    ARG_CHECK((size_t)rows * hidden * 2 <= max_message_bytes, "peer_allreduce_norm: message of %zu bytes exceeds the region", (size_t)rows * hidden * 2);
+    ARG_CHECK((((uintptr_t)in | (uintptr_t)residual | (uintptr_t)gamma | (uintptr_t)y) & 15) == 0, "peer_allreduce_norm: pointers must be 16-byte aligned");
+    if (g_rec) {
+        std::vector<void*> regs(regions, regions + world);
+        return rec_call([=](void* st) {
+            return b200_peer_allreduce_norm(in, residual, gamma, y, is_bf16, rows, hidden, eps, regs.data(), max_message_bytes, rank, world, st);
+        });
+    }
+    PeerArParams p{};
+    p.in = in;
+    int rc = fill_ar_params(p, regions, max_message_bytes, rank, world);
+    if (rc) return rc;
+    p.residual = residual;
+    p.gamma = gamma;
+    p.y = y;
+    p.rows = rows;
+    p.hidden = hidden;
+    p.eps = eps;
+    const size_t smem = (size_t)hidden * sizeof(float) + (size_t)(hidden / 8 / world) * 16;
+    const bool pdl = g_pdl.load() != 0;
+    if (is_bf16)
+        CUDA_CHECK(launch_ex(peer_allreduce_norm_kernel<__nv_bfloat16>, dim3(rows), dim3(kArThreads), smem, (cudaStream_t)stream, pdl, p));
+    else
+        CUDA_CHECK(launch_ex(peer_allreduce_norm_kernel<__half>, dim3(rows), dim3(kArThreads), smem, (cudaStream_t)stream, pdl, p));
+    return launched("peer_allreduce_norm_kernel");
+}
+
+int b200_peer_argmax(const void* logits, int is_bf16, int rows, int vocab_local, int vocab_total, int32_t* out,
+                     void* const* regions, size_t max_message_bytes, int rank, int world, void* stream) {
+    ARG_CHECK(logits && out && regions, "peer_argmax: null pointer");
+    ARG_CHECK(world >= 2 && world <= kArMaxWorld && rank >= 0 && rank < world, "peer_argmax: bad rank/world %d/%d", rank, world);
+    ARG_CHECK(rows > 0 && (size_t)rows * 16 <= max_message_bytes && vocab_local > 0 && vocab_total > 0, "peer_argmax: bad shape");
+    if (g_rec) {
+        std::vector<void*> regs(regions, regions + world);
+        return rec_call([=](void* st) {
+            return b200_peer_argmax(logits, is_bf16, rows, vocab_local, vocab_total, out, regs.data(), max_message_bytes, rank, world, st);
+        });
+    }
+    PeerArParams p{};
+    int rc = fill_ar_params(p, regions, max_message_bytes, rank, world);
+    if (rc) return rc;
+    p.logits = logits;
+    p.token_out = out;
+    p.rows = rows;
+    p.vocab_local = vocab_local;
+    p.vocab_total = vocab_total;
+    const bool pdl = g_pdl.load() != 0;
+    if (is_bf16)
+        CUDA_CHECK(launch_ex(peer_argmax_kernel<__nv_bfloat16>, dim3(rows), dim3(kArThreads), 0, (cudaStream_t)stream, pdl, p));
+    else
+        CUDA_CHECK(launch_ex(peer_argmax_kernel<__half>, dim3(rows), dim3(kArThreads), 0, (cudaStream_t)stream, pdl, p));
+    return launched("peer_argmax_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------ decode programs

@@ -61,7 +61,7 @@ class DecodeStep:
 
     def __init__(self, cfg: ModelConfig, batch: int, ctx: int, device: torch.device, tp_rank: int = 0, tp_size: int = 1,
                  dtype=torch.float16, seed: int = 0, keep_reference: bool = False, ragged: bool = False,
-                 pdl: bool = False, comm=None, fuse_silu: bool = True):
+                 pdl: bool = False, comm=None, fuse_silu: bool = True, fuse_ar_norm: bool = True):
         assert cfg.head_num % tp_size == 0 and cfg.inter % tp_size == 0
         self.cfg, self.B, self.ctx, self.dev, self.dtype = cfg, batch, ctx, device, dtype
         self.tp_rank, self.tp_size, self.comm, self.pdl = tp_rank, tp_size, comm, pdl
@@ -76,6 +76,7 @@ class DecodeStep:
         self.M = (ctx + T - 1) // T
         self.ref: Dict[str, list] = {} if keep_reference else None
         self.fuse_silu = fuse_silu and self.inter % 64 == 0
+        self.fuse_ar_norm = fuse_ar_norm
         g = torch.Generator(device="cpu").manual_seed(seed * 1000 + 17)
         H = cfg.hidden
 
@@ -163,7 +164,15 @@ class DecodeStep:
         P = batch * self.M + 1
         gk = torch.Generator(device=device).manual_seed(42)
         for L in self.layers:
-            L["kv"] = torch.randn(P, 2, self.Hkv, T, self.D, generator=gk, device=device).to(dtype)
+            if shard_full:
+                # parity runs: the FULL pool (all kv heads) from a common seed, then this rank's heads -- every rank holds
+                # DIFFERENT K/V, so a kv-head mix-up between ranks cannot cancel out against the unsharded oracle
+                full = torch.randn(P, 2, cfg.kv_head_num, T, self.D, generator=gk, device=device).to(dtype)
+                kv_rank = tp_rank if cfg.kv_head_num >= tp_size else tp_rank * cfg.kv_head_num // tp_size
+                L["kv_full"] = full.cpu()
+                L["kv"] = full[:, :, kv_rank * self.Hkv:(kv_rank + 1) * self.Hkv].contiguous()
+            else:
+                L["kv"] = torch.randn(P, 2, self.Hkv, T, self.D, generator=gk, device=device).to(dtype)
         gp = torch.Generator().manual_seed(3)
         perm = torch.randperm(P - 1, generator=gp).to(torch.int32) + 1
         self.block_ids_h = perm.reshape(batch, self.M).contiguous().pin_memory()
@@ -224,8 +233,19 @@ class DecodeStep:
         if self.tp_size > 1:
             self.comm.all_reduce(t)
 
+    def _ar_norm(self, t, gamma):
+        """[TP all-reduce of the row-parallel GEMM output t] + residual add + RMSNorm -> self.x. With the peer communicator the
+        three steps are ONE kernel (b200_peer_allreduce_norm); otherwise all-reduce and fused_add_rmsnorm run separately."""
+        if self.tp_size > 1:
+            fused = getattr(self.comm, "all_reduce_norm", None)
+            if self.fuse_ar_norm and fused is not None and fused(t, self.resid, gamma, self.cfg.eps, self.x):
+                return
+            self.comm.all_reduce(t)
+        ops.add_rmsnorm(t, self.resid, gamma, self.cfg.eps, out=self.x)
+
     def step_core(self):
-        """Everything up to the (local) logits: only C-ABI calls, so it can be recorded into a decode program."""
+        """Everything up to the sampled token (TP1 / peer communicator) or the local logits (NCCL): C-ABI calls only, so it
+        can be recorded into a decode program."""
         cfg = self.cfg
         ops.convert_block_table(self.block_ids, out=self.page_list)
         ops.embedding(self.ids, self.embed, out=self.resid)
@@ -235,28 +255,28 @@ class DecodeStep:
                 ops.add_rmsnorm(self.resid, None, L["ln1"], cfg.eps, out=self.x)
                 first = False
             else:
-                ops.add_rmsnorm(self.proj, self.resid, L["ln1"], cfg.eps, out=self.x)
+                self._ar_norm(self.proj, L["ln1"])          # all-reduce of the previous layer's w2 output rides along
             ops.wo_gemm(self.x, L["qkv"], self.gemm_ws, out=self.qkv, pdl=self.pdl)
             ops.rope_append(self.qkv, L["kv"], self.page_list, self.seq_lens, self.Hq, cfg.rope_base, q_out=self.q)
             ops.paged_decode_attn(self.q, L["kv"], self.page_list, self.seq_lens, self.ctx, self.attn_ws, out=self.attn)
             ops.wo_gemm(self.attn, L["o"], self.gemm_ws, out=self.proj, pdl=self.pdl)
-            self._all_reduce(self.proj)
-            ops.add_rmsnorm(self.proj, self.resid, L["ln2"], cfg.eps, out=self.x)
+            self._ar_norm(self.proj, L["ln2"])
             if self.fuse_silu:     # SiLU(gate)*up in the GEMM epilogue (gate/up columns interleaved at load time)
                 ops.wo_gemm(self.x, L["w13"], self.gemm_ws, out=self.act, pdl=self.pdl, silu_mul=True)
             else:
                 ops.wo_gemm(self.x, L["w13"], self.gemm_ws, out=self.gu, pdl=self.pdl)
                 ops.silu_and_mul(self.gu, out=self.act)
             ops.wo_gemm(self.act, L["w2"], self.gemm_ws, out=self.proj, pdl=self.pdl)
-            self._all_reduce(self.proj)
-        ops.add_rmsnorm(self.proj, self.resid, self.final_ln, cfg.eps, out=self.x)
+        self._ar_norm(self.proj, self.final_ln)
         ops.wo_gemm(self.x, self.lm_head, self.gemm_ws, out=self.logits, pdl=self.pdl)
         if self.tp_size == 1:
             ops.argmax(self.logits, out=self.next_ids)
+        elif hasattr(self.comm, "argmax"):
+            self.comm.argmax(self.logits, cfg.vocab, self.next_ids)     # vocab-parallel greedy sampling, own kernel
 
     def step_tail(self):
-        """TP > 1: gather the vocab-split logits and sample (torch / NCCL plumbing, outside the program)."""
-        if self.tp_size > 1:
+        """TP > 1 with stock NCCL: gather the vocab-split logits and sample (torch plumbing, outside the program)."""
+        if self.tp_size > 1 and not hasattr(self.comm, "argmax"):
             self.comm.all_gather(self.logits_all, self.logits)
             full = self.logits_all.permute(1, 0, 2).reshape(self.B, -1)[:, : self.cfg.vocab]   # drop the sp_0_pad8 columns
             self.next_ids.copy_(torch.argmax(full.float(), dim=-1).to(torch.int32))

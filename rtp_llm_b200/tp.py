@@ -52,7 +52,6 @@ class PeerComm(NcclComm):
                 _lib.check(lib.b200_peer_open(hb, ctypes.byref(p)), "b200_peer_open")
                 ptrs.append(p.value)
         self._regions = (ctypes.c_void_p * self.world)(*ptrs)
-        self._calls = 0
         dist.barrier(group=group)     # every rank has zeroed + mapped every region before the first kernel
 
     def all_reduce(self, t: torch.Tensor) -> None:
@@ -61,9 +60,30 @@ class PeerComm(NcclComm):
         if nbytes > self.MAX_MESSAGE or nbytes % 16 or not t.is_contiguous():
             return super().all_reduce(t)
         _lib.check(self._lib.b200_peer_allreduce(t.data_ptr(), t.data_ptr(), nbytes, 1 if t.dtype == torch.bfloat16 else 0,
-                                                 self._regions, self.MAX_MESSAGE, self._calls & 1, self.rank, self.world,
+                                                 self._regions, self.MAX_MESSAGE, 0, self.rank, self.world,
                                                  torch.cuda.current_stream().cuda_stream), "b200_peer_allreduce")
-        self._calls += 1
+
+    def all_reduce_norm(self, t: torch.Tensor, residual: torch.Tensor, gamma: torch.Tensor, eps: float, out: torch.Tensor) -> bool:
+        """out = rmsnorm(allreduce(t) + residual) * gamma, residual += allreduce(t), in one kernel. Returns False (nothing
+        done) when the shape is outside what the fused kernel covers: the caller then issues the two ops separately."""
+        from . import _lib
+        rows, hidden = t.shape
+        if (rows * hidden * t.element_size() > self.MAX_MESSAGE or hidden % (8 * self.world) or hidden > 8192
+                or not (t.is_contiguous() and residual.is_contiguous() and out.is_contiguous())):
+            return False
+        _lib.check(self._lib.b200_peer_allreduce_norm(t.data_ptr(), residual.data_ptr(), gamma.data_ptr(), out.data_ptr(),
+                                                      1 if t.dtype == torch.bfloat16 else 0, rows, hidden, eps, self._regions,
+                                                      self.MAX_MESSAGE, self.rank, self.world,
+                                                      torch.cuda.current_stream().cuda_stream), "b200_peer_allreduce_norm")
+        return True
+
+    def argmax(self, logits: torch.Tensor, vocab_total: int, out: torch.Tensor) -> None:
+        """Greedy token over the vocab-split logits (rank r holds columns [r*V_local, (r+1)*V_local))."""
+        from . import _lib
+        rows, vloc = logits.shape
+        _lib.check(self._lib.b200_peer_argmax(logits.data_ptr(), 1 if logits.dtype == torch.bfloat16 else 0, rows, vloc,
+                                              vocab_total, out.data_ptr(), self._regions, self.MAX_MESSAGE, self.rank, self.world,
+                                              torch.cuda.current_stream().cuda_stream), "b200_peer_argmax")
 
 
 def make_comm(device: torch.device, group=None, kind: str = "peer"):

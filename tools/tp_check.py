@@ -28,12 +28,18 @@ def main():
                                   inter=1024, vocab=1000)
         model = DecodeStep(cfg, 5, 70, dev, tp_rank=rank, tp_size=world, comm=comm, keep_reference=True, ragged=True, seed=2)
         # the oracle runs unsharded: TP=1 twin with the same seeds (weights are generated full, then sliced per rank)
-        kv_before = [step_oracle._bits(L["kv"]) for L in model.layers]
+        kv_before = None
+        if os.environ.get("TP_PROGRAM", "0") == "1" and hasattr(comm, "argmax"):
+            model.build_program()
         model.capture()
         for _ in range(3):
             model.replay()
         torch.cuda.synchronize()
+        dist.all_gather_into_tensor(model.logits_all, model.logits)
         logits = model.logits_all.permute(1, 0, 2).reshape(model.B, -1)[:, : cfg.vocab].float().cpu().numpy()
+        tok = model.next_ids.cpu().numpy()
+        toks = [None] * world
+        dist.all_gather_object(toks, tok.tolist())
         if rank == 0:
             # assemble the unsharded model view for the oracle
             full = types_ns(model, cfg, kv_before, world)
@@ -41,6 +47,8 @@ def main():
             scale = float(np.sqrt((exp ** 2).mean()))
             err = float(np.abs(logits - exp).max())
             good = err <= 3e-2 * scale + 3e-2
+            # sampled tokens: identical on every rank, equal to the argmax of the gathered logits
+            good &= all(t == toks[0] for t in toks) and toks[0] == np.argmax(logits, axis=-1).tolist()
             ok &= good
             print(f"[{'PASS' if good else 'FAIL'}] tp{world} {quant}: max logit err {err:.4g} (rms {scale:.3g})", flush=True)
     dist.barrier()
@@ -50,7 +58,8 @@ def main():
 
 
 def types_ns(model, cfg, kv_before, world):
-    """An object with the attributes oracle_step() reads, describing the UNSHARDED model."""
+    """An object with the attributes oracle_step() reads, describing the UNSHARDED model (full weights, full KV pool: every
+    rank generated the full pool from a common seed and kept only ITS kv heads, so ranks hold different K/V)."""
     import types
     full = types.SimpleNamespace()
     full.cfg, full.B, full.D = cfg, model.B, model.D
@@ -58,27 +67,8 @@ def types_ns(model, cfg, kv_before, world):
     full.ids_h, full.seq_lens_h, full.block_ids_h = model.ids_h, model.seq_lens_h, model.block_ids_h
     full.embed, full.final_ln = model.embed, model.final_ln
     full.lm_head_ref = model.lm_head_full
-    full.layers = []
-    # KV pools: rank r holds kv heads [r*Hkv_local, ...); gather them to build the full pool
-    pools = []
-    for li, L in enumerate(model.layers):
-        t = L["kv"]
-        gathered = [torch.empty_like(t) for _ in range(world)]
-        pools.append(gathered)
-    full.kv_before = None
-    return _finish(full, model, kv_before, world)
-
-
-def _finish(full, model, kv_before, world):
-    # NOTE: every rank seeded its KV pool identically (seed 42, local head count), so the full pool is the concatenation
-    # over ranks along the kv-head axis of identical tensors: build it from rank 0's copy.
-    import numpy as np
-    kvb = []
-    for li, L in enumerate(model.layers):
-        local = kv_before[li].reshape(L["kv"].shape)
-        kvb.append(np.ascontiguousarray(np.concatenate([local] * world, axis=2)))
-        full.layers.append(dict(ln1=L["ln1"], ln2=L["ln2"], ref=L["full"]))
-    full.kv_before = kvb
+    full.layers = [dict(ln1=L["ln1"], ln2=L["ln2"], ref=L["full"]) for L in model.layers]
+    full.kv_before = [step_oracle._bits(L["kv_full"]) for L in model.layers]
     return full
 
 
