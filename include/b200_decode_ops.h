@@ -139,6 +139,22 @@ int b200_embedding(const int32_t* ids, const void* table, void* out, int is_bf16
 /* greedy sampling: out[r] = argmax(logits[r]) (lowest index on ties; CudaSampleOp.cc:330,453). dtype: 0 fp16, 1 bf16, 2 fp32 */
 int b200_argmax(const void* logits, int dtype, int rows, int vocab, int32_t* out, void* stream);
 
+/* Token sampling: the CUDA path behind sampleGreedy (rtp_llm/models_py/bindings/core/CudaSampleOp.cc:423-463; processLogits
+ * :186-279, flashinferSampleGreedy :287-421; penalty kernels common/kernels/sampling_penalty_kernels.cu:26-53,129-185).
+ * Per row, in this order: temperature (logit *= 1/(T+1e-6)), repetition / presence / frequency penalties over the DISTINCT
+ * tokens of `history` (hist_len[r] valid ids of [rows][hist_stride]), softmax (the probabilities REPLACE the logits, as in the
+ * reference), top-k (keep p >= the k-th largest; top_k <= 0 = no limit; top_k == 1 = argmax, lowest index on ties), top-p
+ * within what is left (smallest set of largest p reaching top_p; |top_p| < 1e-7 or >= 1 = no limit), renormalise, and one
+ * inverse-CDF draw in index order with the caller's uniform[r] in [0, 1).  Same distribution as the reference's flashinfer
+ * rejection sampler, different random stream: the caller owns the randomness, so the op is deterministic and graph-replayable.
+ * process[r] == 0 (do_sample false) skips temperature / penalties for that row. count_ws: [rows][vocab] int32, zero on entry
+ * and on exit (only read with penalties). Optional outputs: token_prob_out[r] (renormalised probability of the drawn token,
+ * for cum_log_probs += log p), probs_out [rows][vocab] (output_all_probs after renormalisation). logits fp32, contiguous. */
+int b200_sample(float* logits, int rows, int vocab, const int32_t* history, const int32_t* hist_len, int hist_stride,
+                int32_t* count_ws, const float* temperature, const float* repetition, const float* presence,
+                const float* frequency, const int32_t* top_k, const float* top_p, const float* uniform, const uint8_t* process,
+                int32_t* token_out, float* token_prob_out, float* probs_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ TP all-reduce over NVLink peer memory */
 
 /* One-shot SUM all-reduce of a small [rows][hidden] fp16/bf16 tensor, the exchange after each row-parallel GEMM

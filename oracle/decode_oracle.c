@@ -474,3 +474,96 @@ void oracle_argmax(const float* logits, int rows, int vocab, int32_t* out) {
         out[r] = best;
     }
 }
+
+
+/* ------------------------------------------------------------------ */
+/* Sampling: restatement of sampleGreedy's CUDA path
+ * (rtp_llm/models_py/bindings/core/CudaSampleOp.cc:423-463; processLogits :186-279; flashinferSampleGreedy :287-421;
+ *  penalty kernels rtp_llm/models_py/bindings/common/kernels/sampling_penalty_kernels.cu:26-53,129-185).
+ * Temperature -> penalties over the distinct history tokens -> softmax (written back over the logits) -> top-k (keep
+ * p >= k-th largest) -> top-p inside what is left -> renormalise -> inverse-CDF draw in index order with uniform[r].
+ * The reference draws with flashinfer's rejection sampler (Philox); the kept set and its renormalised probabilities are
+ * deterministic and pinned by the reference's test vectors (CudaSamplerTest.cc:518-568 top_k = 1; :905-976 penalties +
+ * output_all_probs; :986-1057 do_sample + top_k renormalisation), the draw itself is distribution-equivalent. */
+static int cmp_desc(const void* a, const void* b) {
+    float x = *(const float*)a, y = *(const float*)b;
+    return x < y ? 1 : (x > y ? -1 : 0);
+}
+void oracle_sample(float* logits, int rows, int vocab, const int32_t* history, const int32_t* hist_len, int hist_stride,
+                   const float* temperature, const float* repetition, const float* presence, const float* frequency,
+                   const int32_t* top_k, const float* top_p, const float* uniform, const uint8_t* process, int32_t* token_out,
+                   float* token_prob_out, float* probs_out) {
+    int* cnt = (int*)calloc((size_t)vocab, sizeof(int));
+    float* sorted = (float*)malloc((size_t)vocab * sizeof(float));
+    for (int r = 0; r < rows; ++r) {
+        float* lg = logits + (size_t)r * vocab;
+        const int proc = !process || process[r];
+        if (proc) {
+            if (temperature && temperature[r] != 1.0f) {
+                const float inv_t = 1.0f / (temperature[r] + 1e-6f);
+                for (int i = 0; i < vocab; ++i) lg[i] *= inv_t;
+            }
+            const float rep = repetition ? repetition[r] : 1.f, pre = presence ? presence[r] : 0.f, fre = frequency ? frequency[r] : 0.f;
+            if (history && (rep != 1.f || pre != 0.f || fre != 0.f)) {
+                const int32_t* h = history + (size_t)r * hist_stride;
+                for (int i = 0; i < hist_len[r]; ++i)
+                    if (h[i] >= 0 && h[i] < vocab) cnt[h[i]]++;
+                for (int i = 0; i < hist_len[r]; ++i) {
+                    const int t = h[i];
+                    if (t < 0 || t >= vocab || cnt[t] == 0) continue;
+                    float v = lg[t];
+                    v = v < 0.f ? v * rep : v / rep;
+                    v -= pre;
+                    v -= fre * (float)cnt[t];
+                    lg[t] = v;
+                    cnt[t] = 0;
+                }
+            }
+        }
+        float m = -INFINITY;
+        for (int i = 0; i < vocab; ++i) m = lg[i] > m ? lg[i] : m;
+        double z = 0.0;
+        for (int i = 0; i < vocab; ++i) z += exp((double)lg[i] - m);
+        for (int i = 0; i < vocab; ++i) lg[i] = (float)(exp((double)lg[i] - m) / z);
+        int k = top_k[r];
+        if (k <= 0 || k > vocab) k = vocab;
+        float tp = top_p[r];
+        if (fabsf(tp) < 1e-7f) tp = 1.f;
+        float thr = 0.f;
+        if (k < vocab || tp < 1.f) {
+            memcpy(sorted, lg, (size_t)vocab * sizeof(float));
+            qsort(sorted, (size_t)vocab, sizeof(float), cmp_desc);
+            if (k < vocab) thr = sorted[k - 1];
+            if (tp < 1.f) {
+                double zk = 0.0;
+                for (int i = 0; i < vocab && sorted[i] >= thr; ++i) zk += sorted[i];
+                double acc = 0.0;
+                for (int i = 0; i < vocab && sorted[i] >= thr; ++i) {
+                    acc += sorted[i];
+                    if (acc >= (double)tp * zk) {
+                        thr = sorted[i];
+                        break;
+                    }
+                }
+            }
+        }
+        double total = 0.0;
+        for (int i = 0; i < vocab; ++i) total += lg[i] >= thr ? lg[i] : 0.f;
+        const double target = k == 1 ? 0.0 : (double)uniform[r] * total;
+        double acc = 0.0;
+        int pick = -1;
+        for (int i = 0; i < vocab; ++i) {
+            if (lg[i] >= thr) {
+                acc += lg[i];
+                pick = i;
+                if (acc > target) break;
+            }
+        }
+        token_out[r] = pick;
+        if (token_prob_out) token_prob_out[r] = pick >= 0 ? (float)(lg[pick] / total) : 0.f;
+        if (probs_out)
+            for (int i = 0; i < vocab; ++i) probs_out[(size_t)r * vocab + i] = lg[i] >= thr ? (float)(lg[i] / total) : 0.f;
+    }
+    free(cnt);
+    free(sorted);
+}

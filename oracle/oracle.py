@@ -275,3 +275,23 @@ def argmax(logits: np.ndarray) -> np.ndarray:
     out = np.empty(logits.shape[0], np.int32)
     lib().oracle_argmax(_p(logits), logits.shape[0], logits.shape[1], _p(out))
     return out
+
+
+def sample(logits, top_k, top_p, uniform, temperature=None, history=None, hist_len=None, repetition=None, presence=None,
+           frequency=None, process=None):
+    """sampleGreedy's path on fp32 logits [B, V]. Returns (tokens, token_prob, probs after softmax, renormalised kept probs)."""
+    lg = np.ascontiguousarray(logits, np.float32).copy()
+    B, V = lg.shape
+    f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+    hist = None if history is None else np.ascontiguousarray(history, np.int32)
+    hl = None if hist_len is None else np.ascontiguousarray(hist_len, np.int32)
+    tk, tp, u = np.ascontiguousarray(top_k, np.int32), f32(top_p), f32(uniform)
+    t, rp, pp, fp = f32(temperature), f32(repetition), f32(presence), f32(frequency)
+    pr = None if process is None else np.ascontiguousarray(process, np.uint8)
+    tok = np.empty(B, np.int32)
+    tprob = np.empty(B, np.float32)
+    probs = np.empty((B, V), np.float32)
+    P = lambda a: None if a is None else _p(a)
+    lib().oracle_sample(_p(lg), B, V, P(hist), P(hl), hist.shape[1] if hist is not None else 0, P(t), P(rp), P(pp), P(fp), _p(tk),
+                        _p(tp), _p(u), P(pr), _p(tok), _p(tprob), _p(probs))
+    return tok, tprob, lg, probs

@@ -34,6 +34,7 @@ SIGNATURES = {
     "b200_rope_append": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_float, c_void_p]),
     "b200_embedding": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200_argmax": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b200_sample": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int] + [c_void_p] * 13),
     "b200_peer_ar_region_bytes": (c_size_t, [c_size_t]),
     "b200_peer_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
     "b200_peer_open": (c_int, [c_void_p, c_void_p]),

@@ -21,6 +21,7 @@
 #include "internal.h"
 #include "paged_decode_attn.cuh"
 #include "peer_allreduce.cuh"
+#include "sampling.cuh"
 #include "wo_gemm.cuh"
 
 using namespace b200;
@@ -820,6 +821,43 @@ int b200_argmax(const void* logits, int dtype, int rows, int vocab, int32_t* out
     else
         argmax_kernel<float><<<rows, 1024, 0, (cudaStream_t)stream>>>((const float*)logits, vocab, out);
     return launched("argmax_kernel");
+}
+
+int b200_sample(float* logits, int rows, int vocab, const int32_t* history, const int32_t* hist_len, int hist_stride,
+                int32_t* count_ws, const float* temperature, const float* repetition, const float* presence,
+                const float* frequency, const int32_t* top_k, const float* top_p, const float* uniform, const uint8_t* process,
+                int32_t* token_out, float* token_prob_out, float* probs_out, void* stream) {
+    if (rows == 0) return B200_OK;
+    ARG_CHECK(logits && top_k && top_p && uniform && token_out, "sample: null pointer");
+    ARG_CHECK(rows > 0 && rows <= 65535 && vocab > 0, "sample: bad shape [%d, %d]", rows, vocab);
+    ARG_CHECK(!history || (hist_len && hist_stride > 0), "sample: history needs hist_len and a positive stride");
+    ARG_CHECK(!(repetition || presence || frequency) || (history && count_ws), "sample: penalties need history and count_ws");
+    if (g_rec)
+        return rec_call([=](void* st) {
+            return b200_sample(logits, rows, vocab, history, hist_len, hist_stride, count_ws, temperature, repetition, presence,
+                               frequency, top_k, top_p, uniform, process, token_out, token_prob_out, probs_out, st);
+        });
+    SampleParams p{};
+    p.logits = logits;
+    p.probs_out = probs_out;
+    p.history = history;
+    p.hist_len = hist_len;
+    p.count_ws = count_ws;
+    p.temperature = temperature;
+    p.repetition = repetition;
+    p.presence = presence;
+    p.frequency = frequency;
+    p.top_k = top_k;
+    p.top_p = top_p;
+    p.uniform = uniform;
+    p.process = process;
+    p.token_out = token_out;
+    p.token_prob_out = token_prob_out;
+    p.rows = rows;
+    p.vocab = vocab;
+    p.hist_stride = hist_stride;
+    CUDA_CHECK(launch_ex(sample_kernel, dim3(rows), dim3(kSampleThreads), 0, (cudaStream_t)stream, g_pdl.load() != 0, p));
+    return launched("sample_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------ peer all-reduce

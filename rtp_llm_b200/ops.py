@@ -228,6 +228,28 @@ def argmax(logits, out=None):
     return out
 
 
+def sample(logits: torch.Tensor, top_k: torch.Tensor, top_p: torch.Tensor, uniform: torch.Tensor,
+           temperature: Optional[torch.Tensor] = None, history: Optional[torch.Tensor] = None,
+           hist_len: Optional[torch.Tensor] = None, repetition: Optional[torch.Tensor] = None,
+           presence: Optional[torch.Tensor] = None, frequency: Optional[torch.Tensor] = None,
+           process: Optional[torch.Tensor] = None, count_ws: Optional[torch.Tensor] = None, want_probs: bool = False):
+    """sampleGreedy's CUDA path (CudaSampleOp.cc:423-463) on fp32 logits [B, V], IN PLACE (logits become probabilities).
+    Returns (tokens int32 [B], token_prob fp32 [B], renormalised probs [B, V] or None)."""
+    _cuda_contig(logits, top_k, top_p, uniform, temperature, history, hist_len, repetition, presence, frequency, process, count_ws)
+    if logits.dtype != torch.float32:
+        raise B200Error("sample: logits must be fp32 (the reference sampler runs on fp32 logits)")
+    B, V = logits.shape
+    if (repetition is not None or presence is not None or frequency is not None) and count_ws is None:
+        count_ws = torch.zeros(B, V, dtype=torch.int32, device=logits.device)
+    tok = torch.empty(B, dtype=torch.int32, device=logits.device)
+    tprob = torch.empty(B, dtype=torch.float32, device=logits.device)
+    probs = torch.empty_like(logits) if want_probs else None
+    check(_lib.load().b200_sample(_p(logits), B, V, _p(history), _p(hist_len), history.shape[1] if history is not None else 0,
+                                  _p(count_ws), _p(temperature), _p(repetition), _p(presence), _p(frequency), _p(top_k), _p(top_p),
+                                  _p(uniform), _p(process), _p(tok), _p(tprob), _p(probs), _stream()), "b200_sample")
+    return tok, tprob, probs
+
+
 # ------------------------------------------------------------------------------------------------ decode programs
 class Program:
     """Recorded sequence of op calls (b200_program_*): `with prog.record(): <ops...>` then `prog.launch()` replays them
