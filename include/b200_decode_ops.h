@@ -134,6 +134,31 @@ int b200_silu_and_mul(const void* gate_up, void* y, int is_bf16, int rows, int i
 int b200_rope_append(const void* qkv, void* q_out, void* kv_pool, const int32_t* page_list,
                      const int32_t* sequence_lengths, int is_bf16, int batch, int head_num, int kv_head_num,
                      int head_dim, int max_blocks_per_seq, int page_size, float rope_base, void* stream);
+/* The full decode contract of FusedRopeKVCacheDecodeOp.forward (rtp_llm/ops/fused_rope_kvcache_op.py:202-246; device code
+ * rtp_llm/models_py/bindings/common/kernels/rotary_position_embedding.h:322-442,889-1062). b200_rope_config mirrors the
+ * fields of RopeConfig (rtp_llm/cpp/model_utils/RopeConfig.h:21-42) the decode path reads.
+ *   position_ids     optional [batch]; an entry > 0 replaces sequence_lengths[b] as the rotation position (:1040-1042);
+ *                    K/V are still appended at slot sequence_lengths[b]
+ *   cos_sin_cache    optional float2 [cache_positions][dim/2] = (cos, sin), the layout getRopeCache produces with
+ *                    interleave = true (cpp/model_utils/RopeCache.cc:16-85; used for Base and Yarn); without it the
+ *                    coefficients are computed in the kernel with the reference's formulas
+ *   styles           0 No, 1 Base (linear scale), 3 DynamicNTK, 4 QwenDynamicNTK, 5 Yarn, 6 Llama3, 7 Mrope (as Base);
+ *                    factor1 / factor2 = beta_slow / beta_fast (Yarn) or low / high frequency factor (Llama3); max_pos =
+ *                    original_max_position_embeddings
+ *   qkv_bias         optional [(head_num + 2 kv_head_num) * head_dim], added before the rotation
+ *   use_logn_attn    q *= log(pos + 1) / log(max_pos) for pos > max_pos
+ * NeoX pairing (i, i + dim/2) within the first `dim` channels of a head; the rest pass through. */
+typedef struct b200_rope_config {
+    int style;
+    int dim;
+    float base, scale, factor1, factor2;
+    int max_pos;
+    float extrapolation_factor, mscale;
+} b200_rope_config;
+int b200_rope_append_ex(const void* qkv, const void* qkv_bias, void* q_out, void* kv_pool, const int32_t* page_list,
+                        const int32_t* sequence_lengths, const int32_t* position_ids, const float* cos_sin_cache,
+                        int cache_positions, const b200_rope_config* cfg, int use_logn_attn, int is_bf16, int batch, int head_num,
+                        int kv_head_num, int head_dim, int max_blocks_per_seq, int page_size, void* stream);
 /* embedding gather out[b] = table[ids[b]] (rtp_ops.embedding). */
 int b200_embedding(const int32_t* ids, const void* table, void* out, int is_bf16, int rows, int hidden, void* stream);
 /* greedy sampling: out[r] = argmax(logits[r]) (lowest index on ties; CudaSampleOp.cc:330,453). dtype: 0 fp16, 1 bf16, 2 fp32 */

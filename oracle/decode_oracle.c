@@ -567,3 +567,114 @@ void oracle_sample(float* logits, int rows, int vocab, const int32_t* history, c
     free(cnt);
     free(sorted);
 }
+
+
+/* ------------------------------------------------------------------ */
+/* The full decode RoPE contract (fused_rope_kvcache_op.py:202-246; rotary_position_embedding.h:322-442,889-1062;
+ * logn: decoder_masked_multihead_attention_utils.h:2097-2102). Same argument meaning as b200_rope_append_ex. */
+typedef struct {
+    int style, dim;
+    float base, scale, factor1, factor2;
+    int max_pos;
+    float extrapolation_factor, mscale;
+} oracle_rope_config;
+
+static void oracle_rope_coef(const oracle_rope_config* c, int zid, int pos, float* cs, float* sn) {
+    float base = c->base;
+    const int seq_len = pos + 1;
+    if (c->style == 3 && seq_len > c->max_pos)
+        base = c->base * powf((c->scale * seq_len / c->max_pos) - (c->scale - 1.f), c->dim / (c->dim - 2.0f));
+    if (c->style == 4 && seq_len > c->max_pos) {
+        const float ctx = logf((float)seq_len / c->max_pos) / logf(2.0f) + 1.0f;
+        float ntk = powf(2.0f, ceilf(ctx)) - 1.f;
+        if (ntk < 1.0f) ntk = 1.0f;
+        base = c->base * powf(ntk, (float)c->dim / (c->dim - 2));
+    }
+    float a = (float)pos / powf(base, zid / (float)c->dim);
+    float sc = 1.f;
+    if (c->style == 1 || c->style == 7) {
+        a = a / c->scale;
+    } else if (c->style == 5) {
+        const float pi = 3.141592654f;
+        const float t1 = 2.f * logf((float)(int)c->base);
+        int low = (int)floorf(c->dim * logf((float)c->max_pos / (c->factor2 * 2 * pi)) / t1);
+        int high = (int)ceilf(c->dim * logf((float)c->max_pos / (c->factor1 * 2 * pi)) / t1);
+        float lo = (float)(low > 0 ? low : 0), hi = (float)(high < c->dim - 1 ? high : c->dim - 1);
+        if (lo == hi) hi += 0.001f;
+        float ramp = (zid / 2 - lo) / (hi - lo);
+        ramp = ramp < 0.f ? 0.f : (ramp > 1.f ? 1.f : ramp);
+        const float mask = (1.f - ramp) * c->extrapolation_factor;
+        a = (a / c->scale) * (1.f - mask) + a * mask;
+        sc = c->mscale;
+    } else if (c->style == 6) {
+        const float pi = 3.141592654f;
+        const float wavelen = 2 * pi / a;
+        const float low_w = c->max_pos / c->factor1, high_w = c->max_pos / c->factor2;
+        if (wavelen < high_w) {
+        } else if (wavelen > low_w) {
+            a = a / c->scale;
+        } else {
+            const float smooth = (c->max_pos / wavelen - c->factor1) / (c->factor2 - c->factor1);
+            a = (1 - smooth) * a / c->scale + smooth * a;
+        }
+    }
+    *cs = sc * cosf(a);
+    *sn = sc * sinf(a);
+}
+
+void oracle_rope_append_ex(const h16* qkv, const h16* bias, h16* q_out, h16* kv_pool, const int32_t* page_list,
+                           const int32_t* sequence_lengths, const int32_t* position_ids, const float* cos_sin_cache,
+                           int cache_positions, const oracle_rope_config* cfg, int use_logn, int is_bf16, int batch,
+                           int head_num, int kv_head_num, int head_dim, int max_blocks, int tokens_per_block) {
+    const int rhalf = cfg->dim / 2;
+    const size_t page_elems = (size_t)kv_head_num * tokens_per_block * head_dim;
+    for (int b = 0; b < batch; ++b) {
+        const int slot = sequence_lengths[b];
+        const int pos = (position_ids && position_ids[b] > 0) ? position_ids[b] : slot;
+        const h16* row = qkv + (size_t)b * (head_num + 2 * kv_head_num) * head_dim;
+        for (int h = 0; h < head_num + 2 * kv_head_num; ++h) {
+            const h16* src = row + (size_t)h * head_dim;
+            const int is_q = h < head_num, is_v = h >= head_num + kv_head_num;
+            h16* dst;
+            if (is_q) {
+                dst = q_out + ((size_t)b * head_num + h) * head_dim;
+            } else {
+                const int kvh = is_v ? h - head_num - kv_head_num : h - head_num;
+                const int32_t page = page_list[((size_t)b * 2 + (is_v ? 1 : 0)) * max_blocks + slot / tokens_per_block];
+                dst = kv_pool + (size_t)page * page_elems + ((size_t)kvh * tokens_per_block + slot % tokens_per_block) * head_dim;
+            }
+            const int rotate = cfg->style != 0 && !is_v;
+            const float logn = (is_q && use_logn && pos > cfg->max_pos) ? logf((float)(pos + 1)) / logf((float)cfg->max_pos) : 1.f;
+            for (int c = 0; c < head_dim; ++c) {
+                float v = elem_to_float(src[c], is_bf16);
+                if (bias) v = round_elem(v + elem_to_float(bias[(size_t)h * head_dim + c], is_bf16), is_bf16);
+                if (c >= cfg->dim) dst[c] = float_to_elem(logn != 1.f ? v * logn : v, is_bf16);
+            }
+            for (int i = 0; i < rhalf; ++i) {
+                float x0 = elem_to_float(src[i], is_bf16), x1 = elem_to_float(src[i + rhalf], is_bf16);
+                if (bias) {
+                    x0 = round_elem(x0 + elem_to_float(bias[(size_t)h * head_dim + i], is_bf16), is_bf16);
+                    x1 = round_elem(x1 + elem_to_float(bias[(size_t)h * head_dim + i + rhalf], is_bf16), is_bf16);
+                }
+                if (rotate) {
+                    float cs, sn;
+                    if (cos_sin_cache && pos < cache_positions) {
+                        cs = cos_sin_cache[((size_t)pos * rhalf + i) * 2];
+                        sn = cos_sin_cache[((size_t)pos * rhalf + i) * 2 + 1];
+                    } else {
+                        oracle_rope_coef(cfg, 2 * i, pos, &cs, &sn);
+                    }
+                    const float r0 = cs * x0 - sn * x1, r1 = cs * x1 + sn * x0;
+                    x0 = r0;
+                    x1 = r1;
+                }
+                if (logn != 1.f) {
+                    x0 *= logn;
+                    x1 *= logn;
+                }
+                dst[i] = float_to_elem(x0, is_bf16);
+                dst[i + rhalf] = float_to_elem(x1, is_bf16);
+            }
+        }
+    }
+}

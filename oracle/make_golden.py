@@ -206,6 +206,56 @@ def gen_rope():
         print(name, tuple(q_ref.shape), tuple(k_ref.shape))
 
 
+def gen_rope_cache_styles():
+    """Cache path of the decode rope op (Base with linear scale, Yarn): the cos/sin table is built exactly as
+    cpp/model_utils/RopeCache.cc:16-85 builds it (the same torch calls, on CPU), re-laid out as [pos, (cos half | sin half)]
+    for the reference's pure-torch apply_rope_reference (test_mha_rotary_emb.py:121-165), which produces the expected values."""
+    path = f"{REF}/rtp_llm/models_py/modules/factory/attention/cuda_impl/test/test_flashinfer_prefill/test_mha_rotary_emb.py"
+    (apply_rope_reference,) = _ref_functions(path, ["apply_rope_reference"])
+
+    def base_cache(dim, theta, scale, max_pos):          # RopeCache.cc:16-44
+        inv_freq = 1.0 / torch.pow(torch.tensor(float(theta)), torch.arange(0, dim, 2).float() / dim)
+        t = torch.arange(int(max_pos * scale)).float()
+        t.div_(scale)
+        freqs = torch.outer(t, inv_freq)
+        return freqs.cos(), freqs.sin()
+
+    def yarn_cache(dim, theta, scale, max_pos, beta_slow, beta_fast, extrapolation_factor, mscale):   # RopeCache.cc:46-85
+        pos_freqs = torch.pow(torch.tensor(float(theta)), torch.arange(0, dim, 2).float() / dim)
+        inv_e, inv_i = 1.0 / pos_freqs, 1.0 / (scale * pos_freqs)
+        corr = lambda nrot: float(dim * math.log(max_pos / (nrot * 2.0 * math.pi))) / (2.0 * math.log(theta))
+        low = float(max(0, int(math.floor(corr(beta_slow)))))
+        high = float(min(dim - 1, int(math.ceil(corr(beta_fast)))))
+        if abs(low - high) < 1e-6:
+            high += 0.001
+        ramp = torch.clamp((torch.arange(dim // 2).float() - low) / (high - low), 0, 1)
+        mask = (1.0 - ramp) * extrapolation_factor
+        inv_freq = inv_i * (1.0 - mask) + inv_e * mask
+        freqs = torch.outer(torch.arange(int(max_pos * scale)).float(), inv_freq)
+        return freqs.cos() * mscale, freqs.sin() * mscale
+
+    g = torch.Generator().manual_seed(11)
+    cases = [("rope_cache_base_scale2", dict(style=1, dim=128, base=10000.0, scale=2.0, factor1=1.0, factor2=1.0, max_pos=2048,
+                                             extrapolation_factor=1.0, mscale=1.0), base_cache(128, 10000, 2.0, 2048)),
+             ("rope_cache_yarn", dict(style=5, dim=128, base=10000.0, scale=4.0, factor1=1.0, factor2=32.0, max_pos=1024,
+                                      extrapolation_factor=1.0, mscale=1.13), yarn_cache(128, 10000, 4.0, 1024, 1, 32, 1.0, 1.13))]
+    for name, cfg, (cos, sin) in cases:
+        B, Hq, Hkv, D = 4, 4, 2, 128
+        qkv = torch.randn(B, (Hq + 2 * Hkv) * D, generator=g).half()
+        npos = cos.shape[0]
+        positions = torch.randint(1, npos, (B,), generator=g)
+        positions[-1] = npos - 1
+        cache = torch.cat([cos, sin], dim=-1)
+        q = qkv[:, : Hq * D].reshape(B, Hq, D)
+        k = qkv[:, Hq * D:(Hq + Hkv) * D].reshape(B, Hkv, D)
+        q_ref, k_ref = apply_rope_reference(q.float(), k.float(), cache.float(), positions)
+        inter = torch.stack([cos, sin], dim=-1).reshape(npos, -1).contiguous()      # getRopeCache(interleave = true) layout
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), qkv=qkv.numpy(), positions=positions.numpy().astype(np.int32),
+                            q_rope=q_ref.half().numpy(), k_rope=k_ref.half().numpy(), cache_rows=inter[positions].numpy(), cache_positions=npos,
+                            head_num=Hq, kv_head_num=Hkv, head_dim=D, **{f"cfg_{k}": v for k, v in cfg.items()})
+        print(name, tuple(inter.shape))
+
+
 def gen_indexing():
     """Expected values built the way the reference tests build them."""
     rng = np.random.default_rng(42)
@@ -242,4 +292,5 @@ if __name__ == "__main__":
     gen_quant(dev)
     gen_attention(att)
     gen_rope()
+    gen_rope_cache_styles()
     gen_indexing()

@@ -295,3 +295,56 @@ def sample(logits, top_k, top_p, uniform, temperature=None, history=None, hist_l
     lib().oracle_sample(_p(lg), B, V, P(hist), P(hl), hist.shape[1] if hist is not None else 0, P(t), P(rp), P(pp), P(fp), _p(tk),
                         _p(tp), _p(u), P(pr), _p(tok), _p(tprob), _p(probs))
     return tok, tprob, lg, probs
+
+
+class RopeConfig(ctypes.Structure):
+    _fields_ = [("style", ctypes.c_int), ("dim", ctypes.c_int), ("base", ctypes.c_float), ("scale", ctypes.c_float),
+                ("factor1", ctypes.c_float), ("factor2", ctypes.c_float), ("max_pos", ctypes.c_int),
+                ("extrapolation_factor", ctypes.c_float), ("mscale", ctypes.c_float)]
+
+
+def rope_append_ex(qkv_bits, kv_pool_bits, page_list, sequence_lengths, head_num, kv_head_num, head_dim, tokens_per_block, cfg,
+                   bias_bits=None, position_ids=None, cos_sin_cache=None, use_logn=False, is_bf16=False):
+    """The full decode rope contract (b200_rope_append_ex). cfg: dict of RopeConfig fields. Returns (q_out bits, pool copy)."""
+    qkv = np.ascontiguousarray(qkv_bits, np.uint16)
+    pool = np.ascontiguousarray(kv_pool_bits, np.uint16).copy()
+    page_list = np.ascontiguousarray(page_list, np.int32)
+    seq = np.ascontiguousarray(sequence_lengths, np.int32)
+    B = qkv.shape[0]
+    q_out = np.empty((B, head_num * head_dim), np.uint16)
+    rc = RopeConfig(**cfg)
+    bias = None if bias_bits is None else np.ascontiguousarray(bias_bits, np.uint16)
+    pid = None if position_ids is None else np.ascontiguousarray(position_ids, np.int32)
+    cache = None if cos_sin_cache is None else np.ascontiguousarray(cos_sin_cache, np.float32)
+    P = lambda a: None if a is None else _p(a)
+    lib().oracle_rope_append_ex(_p(qkv), P(bias), _p(q_out), _p(pool), _p(page_list), _p(seq), P(pid), P(cache),
+                                cache.shape[0] if cache is not None else 0, ctypes.byref(rc), int(use_logn), int(is_bf16), B, head_num,
+                                kv_head_num, head_dim, page_list.shape[-1], tokens_per_block)
+    return q_out, pool
+
+
+def rope_cache_base(dim, theta, scale, max_pos):
+    """genBaseCache (cpp/model_utils/RopeCache.cc:16-44), interleave = true: fp32 [positions, dim] = (cos, sin) pairs."""
+    inv_freq = (1.0 / np.power(np.float32(theta), np.arange(0, dim, 2, dtype=np.float32) / np.float32(dim))).astype(np.float32)
+    t = (np.arange(int(max_pos * scale), dtype=np.float32) / np.float32(scale)).astype(np.float32)
+    freqs = np.outer(t, inv_freq).astype(np.float32)
+    return np.stack([np.cos(freqs), np.sin(freqs)], axis=-1).reshape(freqs.shape[0], -1).astype(np.float32)
+
+
+def rope_cache_yarn(dim, theta, scale, max_pos, beta_slow, beta_fast, extrapolation_factor, mscale):
+    """genYarnCache (RopeCache.cc:46-85), interleave = true."""
+    pos_freqs = np.power(np.float32(theta), np.arange(0, dim, 2, dtype=np.float32) / np.float32(dim)).astype(np.float32)
+    inv_e, inv_i = (1.0 / pos_freqs).astype(np.float32), (1.0 / (np.float32(scale) * pos_freqs)).astype(np.float32)
+
+    def corr(nrot):
+        return np.float32(dim * np.log(np.float32(max_pos / (nrot * 2.0 * np.pi)))) / (2.0 * np.log(np.float32(theta)))
+    low = float(max(0, int(np.floor(corr(beta_slow)))))
+    high = float(min(dim - 1, int(np.ceil(corr(beta_fast)))))
+    if abs(low - high) < 1e-6:
+        high += 0.001
+    ramp = np.clip((np.arange(dim // 2, dtype=np.float32) - low) / (high - low), 0, 1).astype(np.float32)
+    mask = ((1.0 - ramp) * extrapolation_factor).astype(np.float32)
+    inv_freq = (inv_i * (1.0 - mask) + inv_e * mask).astype(np.float32)
+    t = np.arange(int(max_pos * scale), dtype=np.float32)
+    freqs = np.outer(t, inv_freq).astype(np.float32)
+    return (np.stack([np.cos(freqs), np.sin(freqs)], axis=-1).reshape(freqs.shape[0], -1) * np.float32(mscale)).astype(np.float32)

@@ -32,6 +32,7 @@ SIGNATURES = {
     "b200_add_rmsnorm": (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_float, c_void_p]),
     "b200_silu_and_mul": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200_rope_append": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_float, c_void_p]),
+    "b200_rope_append_ex": (c_int, [c_void_p] * 8 + [c_int, c_void_p] + [c_int] * 8 + [c_void_p]),
     "b200_embedding": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200_argmax": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200_sample": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int] + [c_void_p] * 13),
@@ -50,6 +51,14 @@ SIGNATURES = {
     "b200_program_set_trace": (c_int, [c_void_p, c_void_p]),
     "b200_program_destroy": (c_int, [c_void_p]),
 }
+
+
+
+class RopeConfig(ctypes.Structure):
+    """b200_rope_config (include/b200_decode_ops.h) = the RopeConfig fields the decode path reads (RopeConfig.h:21-42)."""
+    _fields_ = [("style", c_int), ("dim", c_int), ("base", c_float), ("scale", c_float), ("factor1", c_float), ("factor2", c_float),
+                ("max_pos", c_int), ("extrapolation_factor", c_float), ("mscale", c_float)]
+
 
 _lib = None
 

@@ -217,6 +217,122 @@ __global__ void rope_append_kernel(const T* __restrict__ qkv, T* __restrict__ q_
     }
 }
 
+
+// ---- the full decode RoPE contract of FusedRopeKVCacheDecodeOp (rtp_llm/ops/fused_rope_kvcache_op.py:202-246 ->
+// decode_fused_rope_kvcache; device code rtp_llm/models_py/bindings/common/kernels/rotary_position_embedding.h):
+//   position      sequence_lengths[b], overridden by position_ids[b] when that is > 0              (:1040-1042)
+//   coefficient   cos_sin_cache[pos * dim/2 + i] when a cache is given (Base / Yarn: cpp/model_utils/RopeCache.cc:16-85), else
+//                 angle = pos / powf(base, 2i/dim) transformed per style (:322-440), (cos, sin) scaled by mscale (Yarn)
+//   styles        Base / Mrope (linear scale), DynamicNTK, QwenDynamicNTK (base rescaled when pos+1 > max_pos, :889-903),
+//                 Yarn (:365-419), Llama3 (:421-442)
+//   pairing       NeoX halves (i, i + dim/2) inside the first `dim` channels of a head; channels >= dim pass through
+//   bias          optional qkv bias added (in the tensor type) before the rotation
+//   logn          q *= log(pos + 1) / log(max_pos) when pos > max_pos (decoder_masked_multihead_attention_utils.h:2097-2102)
+struct RopeCfg {
+    int style;      // RopeStyle (cpp/model_utils/RopeConfig.h:7-16): 0 No, 1 Base, 3 DynamicNTK, 4 QwenDynamicNTK, 5 Yarn, 6 Llama3, 7 Mrope
+    int dim;        // rotary dim (<= head_dim)
+    float base, scale, factor1, factor2;
+    int max_pos;
+    float extrapolation_factor, mscale;
+};
+
+__device__ __forceinline__ float2 rope_coef(const RopeCfg& c, int zid, int pos) {
+    float base = c.base;
+    const int seq_len = pos + 1;
+    if (c.style == 3 && seq_len > c.max_pos)
+        base = c.base * powf((c.scale * seq_len / c.max_pos) - (c.scale - 1.f), c.dim / (c.dim - 2.0f));
+    if (c.style == 4 && seq_len > c.max_pos) {
+        const float ctx = logf((float)seq_len / c.max_pos) / logf(2.0f) + 1.0f;
+        const float ntk = fmaxf(powf(2.0f, ceilf(ctx)) - 1.f, 1.0f);
+        base = c.base * powf(ntk, (float)c.dim / (c.dim - 2));
+    }
+    float a = (float)pos / powf(base, zid / (float)c.dim);
+    float sc = 1.f;
+    if (c.style == 1 || c.style == 7) {
+        a = a / c.scale;
+    } else if (c.style == 5) {
+        const float pi = 3.141592654f;
+        const int ibase = (int)c.base;
+        const float t1 = 2.f * logf((float)ibase);
+        int low = (int)floorf(c.dim * logf((float)c.max_pos / (c.factor2 * 2 * pi)) / t1);
+        int high = (int)ceilf(c.dim * logf((float)c.max_pos / (c.factor1 * 2 * pi)) / t1);
+        float lo = (float)max(low, 0), hi = (float)min(high, c.dim - 1);
+        if (lo == hi) hi += 0.001f;
+        const float ramp = fminf(1.f, fmaxf(0.f, (zid / 2 - lo) / (hi - lo)));
+        const float mask = (1.f - ramp) * c.extrapolation_factor;
+        a = (a / c.scale) * (1.f - mask) + a * mask;
+        sc = c.mscale;
+    } else if (c.style == 6) {
+        const float pi = 3.141592654f;
+        const float wavelen = 2 * pi / a;
+        const float low_w = c.max_pos / c.factor1, high_w = c.max_pos / c.factor2;
+        if (wavelen < high_w) {
+        } else if (wavelen > low_w) {
+            a = a / c.scale;
+        } else {
+            const float smooth = (c.max_pos / wavelen - c.factor1) / (c.factor2 - c.factor1);
+            a = (1 - smooth) * a / c.scale + smooth * a;
+        }
+    }
+    float sn, cs;
+    sincosf(a, &sn, &cs);
+    return make_float2(sc * cs, sc * sn);
+}
+
+template <typename T>
+__global__ void rope_append_ex_kernel(const T* __restrict__ qkv, const T* __restrict__ bias, T* __restrict__ q_out,
+                                      T* __restrict__ kv_pool, const int32_t* __restrict__ page_list,
+                                      const int32_t* __restrict__ seq_lens, const int32_t* __restrict__ position_ids,
+                                      const float2* __restrict__ cos_sin_cache, int cache_positions, RopeCfg cfg, int use_logn,
+                                      int head_num, int kv_head_num, int head_dim, int max_blocks, int tokens_per_block) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int b = blockIdx.x, h = blockIdx.y, i = threadIdx.x, half = head_dim / 2, rhalf = cfg.dim / 2;
+    const int slot = seq_lens[b];                                  // where K/V of the new token go (tokens already cached)
+    const int pos = (position_ids && position_ids[b] > 0) ? position_ids[b] : slot;
+    const T* src = qkv + ((size_t)b * (head_num + 2 * kv_head_num) + h) * head_dim;
+    const T* bsrc = bias ? bias + (size_t)h * head_dim : nullptr;
+    const size_t page_elems = (size_t)kv_head_num * tokens_per_block * head_dim;
+    T* dst;
+    bool rotate = cfg.style != 0, is_q = h < head_num;
+    if (is_q) {
+        dst = q_out + ((size_t)b * head_num + h) * head_dim;
+    } else {
+        const bool is_v = h >= head_num + kv_head_num;
+        const int kvh = is_v ? h - head_num - kv_head_num : h - head_num;
+        const int32_t page = page_list[((size_t)b * 2 + (is_v ? 1 : 0)) * max_blocks + slot / tokens_per_block];
+        dst = kv_pool + (size_t)page * page_elems + ((size_t)kvh * tokens_per_block + slot % tokens_per_block) * head_dim;
+        rotate = rotate && !is_v;
+    }
+    // thread i owns the channel pair (i, i + dim/2) for i < dim/2, and the pass-through channels dim + i, dim + i + (head_dim-dim)/2 ...
+    auto load = [&](int c) {
+        float v = to_f32<T>(src[c]);
+        if (bsrc) v = to_f32<T>(from_f32<T>(v + to_f32<T>(bsrc[c])));
+        return v;
+    };
+    if (i < rhalf) {
+        float x0 = load(i), x1 = load(i + rhalf);
+        if (rotate) {
+            const float2 cf = (cos_sin_cache && pos < cache_positions) ? cos_sin_cache[(size_t)pos * rhalf + i] : rope_coef(cfg, 2 * i, pos);
+            const float r0 = cf.x * x0 - cf.y * x1, r1 = cf.x * x1 + cf.y * x0;
+            x0 = r0;
+            x1 = r1;
+        }
+        if (is_q && use_logn && pos > cfg.max_pos) {
+            const float logn = logf((float)(pos + 1)) / logf((float)cfg.max_pos);
+            x0 *= logn;
+            x1 *= logn;
+        }
+        dst[i] = from_f32<T>(x0);
+        dst[i + rhalf] = from_f32<T>(x1);
+    }
+    for (int c = cfg.dim + i; c < head_dim; c += half) {            // channels beyond the rotary dim
+        float v = load(c);
+        if (is_q && use_logn && pos > cfg.max_pos) v *= logf((float)(pos + 1)) / logf((float)cfg.max_pos);
+        dst[c] = from_f32<T>(v);
+    }
+}
+
 // token embedding gather: out[b][:] = table[ids[b]][:]
 template <typename T>
 __global__ void embedding_kernel(const int32_t* __restrict__ ids, const T* __restrict__ table, T* __restrict__ out,

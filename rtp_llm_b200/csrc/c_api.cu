@@ -788,6 +788,42 @@ int b200_rope_append(const void* qkv, void* q_out, void* kv_pool, const int32_t*
     return launched("rope_append_kernel");
 }
 
+int b200_rope_append_ex(const void* qkv, const void* qkv_bias, void* q_out, void* kv_pool, const int32_t* page_list,
+                        const int32_t* sequence_lengths, const int32_t* position_ids, const float* cos_sin_cache,
+                        int cache_positions, const b200_rope_config* cfg, int use_logn_attn, int is_bf16, int batch, int head_num,
+                        int kv_head_num, int head_dim, int max_blocks_per_seq, int page_size, void* stream) {
+    if (batch == 0) return B200_OK;
+    ARG_CHECK(qkv && q_out && kv_pool && page_list && sequence_lengths && cfg, "rope_append_ex: null pointer");
+    ARG_CHECK(head_dim > 0 && head_dim % 2 == 0 && head_dim <= 512, "rope_append_ex: head_dim %d unsupported", head_dim);
+    ARG_CHECK(cfg->style == 0 || (cfg->style >= 1 && cfg->style <= 7 && cfg->style != 2), "rope_append_ex: rope style %d unsupported (Glm2 is out of scope)", cfg->style);
+    ARG_CHECK(cfg->dim > 0 && cfg->dim % 2 == 0 && cfg->dim <= head_dim, "rope_append_ex: rotary dim %d must be even and <= head_dim", cfg->dim);
+    ARG_CHECK(cfg->style == 0 || cfg->base > 1.f, "rope_append_ex: rope base must be > 1");
+    ARG_CHECK(!cos_sin_cache || cache_positions > 0, "rope_append_ex: a cos/sin cache needs its number of positions");
+    ARG_CHECK(!use_logn_attn || cfg->max_pos > 1, "rope_append_ex: logn attention needs max_pos > 1");
+    const b200_rope_config cc = *cfg;
+    if (g_rec)
+        return rec_call([=](void* st) {
+            return b200_rope_append_ex(qkv, qkv_bias, q_out, kv_pool, page_list, sequence_lengths, position_ids, cos_sin_cache,
+                                       cache_positions, &cc, use_logn_attn, is_bf16, batch, head_num, kv_head_num, head_dim,
+                                       max_blocks_per_seq, page_size, st);
+        });
+    RopeCfg rc{cc.style, cc.dim, cc.base, cc.scale, cc.factor1, cc.factor2, cc.max_pos, cc.extrapolation_factor, cc.mscale};
+    const dim3 grid(batch, head_num + 2 * kv_head_num);
+    const bool pdl = g_pdl.load() != 0;
+    const float2* cache = reinterpret_cast<const float2*>(cos_sin_cache);
+    if (is_bf16)
+        CUDA_CHECK(launch_ex(rope_append_ex_kernel<__nv_bfloat16>, grid, dim3(head_dim / 2), 0, (cudaStream_t)stream, pdl,
+                             (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)qkv_bias, (__nv_bfloat16*)q_out, (__nv_bfloat16*)kv_pool,
+                             page_list, sequence_lengths, position_ids, cache, cache_positions, rc, use_logn_attn, head_num,
+                             kv_head_num, head_dim, max_blocks_per_seq, page_size));
+    else
+        CUDA_CHECK(launch_ex(rope_append_ex_kernel<__half>, grid, dim3(head_dim / 2), 0, (cudaStream_t)stream, pdl, (const __half*)qkv,
+                             (const __half*)qkv_bias, (__half*)q_out, (__half*)kv_pool, page_list, sequence_lengths, position_ids,
+                             cache, cache_positions, rc, use_logn_attn, head_num, kv_head_num, head_dim, max_blocks_per_seq,
+                             page_size));
+    return launched("rope_append_ex_kernel");
+}
+
 int b200_embedding(const int32_t* ids, const void* table, void* out, int is_bf16, int rows, int hidden, void* stream) {
     (void)is_bf16;
     if (rows == 0) return B200_OK;

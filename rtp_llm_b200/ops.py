@@ -209,6 +209,23 @@ def rope_append(qkv, kv_cache_base, page_list, sequence_lengths, head_num, rope_
     return q_out
 
 
+def rope_append_ex(qkv, kv_cache_base, page_list, sequence_lengths, head_num, rope_cfg: "_lib.RopeConfig", q_out=None, bias=None,
+                   position_ids=None, cos_sin_cache=None, use_logn_attn=False):
+    """FusedRopeKVCacheDecodeOp.forward with the whole rope contract (styles, position_ids override, bias, cos/sin cache,
+    logn): see b200_rope_append_ex in include/b200_decode_ops.h. cos_sin_cache: fp32 [positions, dim] interleaved (cos, sin)."""
+    import ctypes
+    _cuda_contig(qkv, kv_cache_base, page_list, sequence_lengths, q_out, bias, position_ids, cos_sin_cache)
+    P, two, Hkv, T, D = kv_cache_base.shape
+    B = qkv.shape[0]
+    if q_out is None:
+        q_out = torch.empty((B, head_num * D), dtype=qkv.dtype, device=qkv.device)
+    check(_lib.load().b200_rope_append_ex(_p(qkv), _p(bias), _p(q_out), _p(kv_cache_base), _p(page_list), _p(sequence_lengths),
+                                          _p(position_ids), _p(cos_sin_cache), cos_sin_cache.shape[0] if cos_sin_cache is not None else 0,
+                                          ctypes.cast(ctypes.pointer(rope_cfg), ctypes.c_void_p), 1 if use_logn_attn else 0,
+                                          _is_bf16(qkv), B, head_num, Hkv, D, page_list.shape[-1], T, _stream()), "b200_rope_append_ex")
+    return q_out
+
+
 def embedding(ids, table, out=None):
     _cuda_contig(ids, table, out)
     rows, hidden = ids.shape[0], table.shape[1]

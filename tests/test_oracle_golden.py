@@ -161,3 +161,71 @@ def test_rope_matches_reference_torch_rope(golden_dir, name):
         np.testing.assert_allclose(pool_f[page, 0, :, slot].astype(np.float32), g["k_rope"][b].astype(np.float32), rtol=1e-2, atol=1e-2)
         v = qkv[b, (Hq + Hkv) * D:].reshape(Hkv, D)
         assert np.array_equal(pool_f[page, 1, :, slot], v)
+
+
+def _rope_case(g):
+    cfg = {k[4:]: (float(g[k]) if g[k].dtype.kind == "f" else int(g[k])) for k in g.files if k.startswith("cfg_")}
+    return cfg, g["qkv"], int(g["head_num"]), int(g["kv_head_num"]), int(g["head_dim"]), g["positions"].astype(np.int32)
+
+
+@pytest.mark.parametrize("name", ["rope_cache_base_scale2", "rope_cache_yarn"])
+def test_rope_ex_cache_and_inline_styles_match_reference(golden_dir, name):
+    """oracle_rope_append_ex against the reference's torch RoPE applied with the cos/sin table RopeCache.cc builds (Base with
+    linear scale, Yarn). The fixture stores the table rows at the sampled positions (built with the reference's torch calls);
+    the oracle's numpy builders must reproduce them, and the op must match (1) through the cache and, for Base, (2) with the
+    coefficients computed inline by the formulas of rotary_position_embedding.h. (For Yarn the reference's table and its
+    in-kernel formula disagree on which of beta_slow / beta_fast bounds the ramp from below -- RopeCache.cc:57-62 vs
+    rotary_position_embedding.h:405-410 --; the decode op uses the table whenever it exists, so the table is what is pinned.)"""
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    cfg, qkv, Hq, Hkv, D, pos = _rope_case(g)
+    if cfg["style"] == 1:
+        cache = orc.rope_cache_base(cfg["dim"], cfg["base"], cfg["scale"], cfg["max_pos"])
+    else:
+        cache = orc.rope_cache_yarn(cfg["dim"], cfg["base"], cfg["scale"], cfg["max_pos"], cfg["factor1"], cfg["factor2"],
+                                    cfg["extrapolation_factor"], cfg["mscale"])
+    assert cache.shape[0] == int(g["cache_positions"])
+    np.testing.assert_allclose(cache[pos], g["cache_rows"], atol=2e-3)     # float32 cos/sin of angles up to ~4e3 rad
+    B, T = qkv.shape[0], 16
+    M = int(pos.max()) // T + 1
+    block_ids = (np.arange(B * M, dtype=np.int32) + 1).reshape(B, M)
+    pl = orc.convert_block_table(block_ids)
+    pool = np.zeros((1 + B * M, 2, Hkv, T, D), np.float16)
+    for c in ((cache, None) if cfg["style"] == 1 else (cache,)):
+        q_out, pool_out = orc.rope_append_ex(qkv.view(np.uint16), pool.view(np.uint16), pl, pos, Hq, Hkv, D, T, cfg, cos_sin_cache=c)
+        np.testing.assert_allclose(orc.from_bits(q_out, False).reshape(B, Hq, D), g["q_rope"].astype(np.float32), rtol=1e-2, atol=1e-2)
+        pf = pool_out.view(np.float16).reshape(pool.shape)
+        for b in range(B):
+            np.testing.assert_allclose(pf[block_ids[b, pos[b] // T], 0, :, pos[b] % T].astype(np.float32),
+                                       g["k_rope"][b].astype(np.float32), rtol=1e-2, atol=1e-2)
+
+
+def test_rope_ex_position_override_bias_logn_and_partial_dim():
+    rng = np.random.default_rng(3)
+    B, Hq, Hkv, D, T, M = 3, 2, 1, 128, 16, 70
+    qkv = rng.standard_normal((B, (Hq + 2 * Hkv) * D)).astype(np.float16)
+    bias = (rng.standard_normal((Hq + 2 * Hkv) * D) * 0.1).astype(np.float16)
+    seq = np.array([5, 40, 1000], np.int32)
+    block_ids = (np.arange(B * M, dtype=np.int32) + 1).reshape(B, M)
+    pl = orc.convert_block_table(block_ids)
+    pool = np.zeros((1 + B * M, 2, Hkv, T, D), np.float16)
+    cfg = dict(style=1, dim=64, base=10000.0, scale=1.0, factor1=1.0, factor2=1.0, max_pos=512, extrapolation_factor=1.0, mscale=1.0)
+    pid = np.array([0, 77, 0], np.int32)                  # entry > 0 overrides the position, 0 keeps sequence_lengths
+    q, pool_o = orc.rope_append_ex(qkv.view(np.uint16), pool.view(np.uint16), pl, seq, Hq, Hkv, D, T, cfg, bias_bits=bias.view(np.uint16),
+                                   position_ids=pid, use_logn=True)
+    qf = orc.from_bits(q, False).reshape(B, Hq, D)
+    xb = (qkv.astype(np.float32) + bias.astype(np.float32)).astype(np.float16).astype(np.float32).reshape(B, Hq + 2 * Hkv, D)
+    for b, p in enumerate((5, 77, 1000)):
+        inv = 1.0 / np.power(10000.0, np.arange(0, 64, 2) / 64.0)
+        c, s_ = np.cos(p * inv), np.sin(p * inv)
+        x = xb[b, 0]
+        exp = x.copy()
+        exp[:32] = x[:32] * c - x[32:64] * s_
+        exp[32:64] = x[32:64] * c + x[:32] * s_
+        if p > 512:
+            exp *= np.log(p + 1) / np.log(512)            # logn scaling of q beyond max_pos
+        np.testing.assert_allclose(qf[b, 0], exp, rtol=2e-3, atol=2e-3)
+        # K is appended at slot sequence_lengths[b] (not at the overridden position), V unrotated with the bias added
+        pf = pool_o.view(np.float16).reshape(pool.shape)
+        page, slot = block_ids[b, seq[b] // T], seq[b] % T
+        np.testing.assert_allclose(pf[page, 1, 0, slot].astype(np.float32), xb[b, Hq + Hkv], atol=1e-3)
+        assert np.abs(pf[page, 0, 0, slot].astype(np.float32)).sum() > 0
