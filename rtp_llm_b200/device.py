@@ -33,7 +33,9 @@ def pack_int8_tensor_to_packed_int4(t: torch.Tensor) -> torch.Tensor:
 
 
 class B200Impl:
-    """Drop-in for CudaImpl's weight hooks. Returned `kernel` tensors carry the packed weight as `._b200_packed`."""
+    """Drop-in for CudaImpl's weight hooks. The returned `kernel` tensors are self-describing blobs (ops.PackedWeight: a
+    trailer inside the tensor names format / K / N), so they survive the loader's `.contiguous().to(device)`, clones and
+    state-dict round trips; B200WeightOnlyLinear rebuilds the description with PackedWeight.from_tensor()."""
 
     def __init__(self, device="cuda", act_dtype=torch.float16):
         self.device, self.act_dtype = torch.device(device), act_dtype
@@ -49,14 +51,14 @@ class B200Impl:
         shape = tensor.shape
         q, scale = self.symmetric_quantize_last_axis_of_batched_matrix(tensor.reshape(shape[0], -1).float())
         packed = ops.pack_w8(q.to(self.device).contiguous(), scale.to(self.act_dtype).to(self.device))
-        kernel = packed.data
-        kernel._b200_packed = packed
-        return kernel, scale.to(self.device)
+        return packed.data, scale.to(self.device)
 
     # -- device_impl.py:242-300
     def unpack_groupwise(self, qweight_int32, qzeros_int32, scales_fp16, gptq: bool, awq: bool, weight_bits: int = 4):
         """Returns the loader's UN-permuted tensors (q_packed uint8 [K,N/2], zeros_x_scales fp16, scales fp16)."""
-        assert weight_bits == 4, "INT8 group-wise checkpoints are outside the built scope"
+        if weight_bits != 4:
+            # device_impl.py:256-262 also accepts 8-bit group-wise checkpoints; the b200 INT8 kernel is per-column only
+            raise ValueError("8-bit group-wise (GPTQ/AWQ W8) checkpoints are outside the built scope: 4-bit group-wise or per-column INT8")
         qweight = qweight_int32.reshape(qweight_int32.shape[0], -1)
         qzeros = qzeros_int32.reshape(qzeros_int32.shape[0], -1)
         scales = scales_fp16.reshape(scales_fp16.shape[0], -1)
@@ -87,6 +89,4 @@ class B200Impl:
         assert scales is not None and zeros_x_scales is not None, "the b200 INT4 blob carries scales and zero*scale"
         packed = ops.pack_w4(tensor.to(self.device).contiguous(), scales.to(self.act_dtype).to(self.device).contiguous(),
                              zeros_x_scales.to(self.act_dtype).to(self.device).contiguous())
-        kernel = packed.data
-        kernel._b200_packed = packed
-        return kernel
+        return packed.data

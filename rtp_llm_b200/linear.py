@@ -72,10 +72,8 @@ class B200WeightOnlyLinear(LinearBase):
             self.packed = ops.pack_f16(weight)
         elif isinstance(weight, ops.PackedWeight):
             self.packed = weight
-        elif hasattr(weight, "_b200_packed"):           # tensor produced by B200Impl.preprocess_* (device.py)
-            self.packed = weight._b200_packed
-        else:
-            raise B200Error("quantised weight is not in the b200 layout: load it through B200Impl (rtp_llm_b200.device)")
+        else:                                           # tensor produced by B200Impl.preprocess_* (device.py), or any copy of it
+            self.packed = ops.PackedWeight.from_tensor(weight)
         if self.packed.fmt == B200_FMT_INT8 and self.packed.col_scale is None:
             self.packed.col_scale = weight_scales
 
@@ -84,6 +82,8 @@ class B200WeightOnlyLinear(LinearBase):
         x = input.reshape(-1, input.shape[-1])
         if not x.is_contiguous():
             x = x.contiguous()
+        if self.packed.col_scale is not None and self.packed.col_scale.dtype != x.dtype:
+            self.packed.col_scale = self.packed.col_scale.to(x.dtype).contiguous()   # the loader keeps INT8 scales in fp32 (device_impl.py:190)
         ws = _workspace(x.device, self.MAX_BATCH, self.packed.K, self.packed.N)
         outs = []
         for i in range(0, x.shape[0], self.MAX_BATCH):   # decode batches are <= 128; larger inputs go in slabs

@@ -98,11 +98,38 @@ def paged_decode_attn(q: torch.Tensor, kv_cache_base: torch.Tensor, page_list: t
 
 
 # ------------------------------------------------------------------------------------------------ weight-only GEMM
+_TRAILER_BYTES = 256
+_TRAILER_MAGIC = 0x42323030574F4731        # "B200WOG1"
+
+
 class PackedWeight:
-    """A weight in the layout b200_wo_gemm consumes (+ what the epilogue needs)."""
+    """A weight in the layout b200_wo_gemm consumes (+ what the epilogue needs).
+
+    Quantised blobs are SELF-DESCRIBING: the uint8 tensor is [blob bytes | 256-byte trailer] with a magic number, the format and
+    (K, N, group). The reference loader hands kernels around as plain tensors and copies them freely
+    (device_impl.py:296-298 `.contiguous().to(device)`, state-dict round trips): a Python attribute on the tensor would be
+    lost there, the trailer travels with the bytes. PackedWeight.from_tensor() rebuilds the description from any copy."""
 
     def __init__(self, fmt: int, K: int, N: int, data: torch.Tensor, col_scale: Optional[torch.Tensor] = None):
         self.fmt, self.K, self.N, self.data, self.col_scale = fmt, K, N, data, col_scale
+
+    @staticmethod
+    def _write_trailer(data: torch.Tensor, fmt: int, K: int, N: int, group: int) -> None:
+        t = torch.tensor([_TRAILER_MAGIC, fmt, K, N, group], dtype=torch.int64)
+        data[-_TRAILER_BYTES:-_TRAILER_BYTES + 40] = t.view(torch.uint8).to(data.device)
+
+    @staticmethod
+    def from_tensor(data: torch.Tensor, col_scale: Optional[torch.Tensor] = None) -> "PackedWeight":
+        if data.dtype != torch.uint8 or data.dim() != 1 or data.numel() <= _TRAILER_BYTES:
+            raise B200Error("not a b200 weight blob (expected a 1-D uint8 tensor with a trailer)")
+        t = data[-_TRAILER_BYTES:-_TRAILER_BYTES + 40].cpu().view(torch.int64).tolist()
+        if t[0] != _TRAILER_MAGIC:
+            raise B200Error("not a b200 weight blob (bad magic): quantised weights must be loaded through B200Impl")
+        fmt, K, N = int(t[1]), int(t[2]), int(t[3])
+        n = int(_lib.load().b200_wo_gemm_packed_bytes(fmt, K, N))
+        if n + _TRAILER_BYTES != data.numel():
+            raise B200Error(f"b200 weight blob has {data.numel()} bytes, expected {n + _TRAILER_BYTES} for K={K} N={N}")
+        return PackedWeight(fmt, K, N, data if data.is_contiguous() else data.contiguous(), col_scale)
 
 
 def pack_w4(q_packed: torch.Tensor, scales: torch.Tensor, zeros_x_scales: torch.Tensor, group: int = 128) -> PackedWeight:
@@ -112,9 +139,10 @@ def pack_w4(q_packed: torch.Tensor, scales: torch.Tensor, zeros_x_scales: torch.
     n = _lib.load().b200_wo_gemm_packed_bytes(B200_FMT_INT4, K, N)
     if n == 0:
         raise B200Error(f"pack_w4: unsupported shape K={K} N={N}")
-    blob = torch.empty(int(n), dtype=torch.uint8, device=q_packed.device)
+    blob = torch.empty(int(n) + _TRAILER_BYTES, dtype=torch.uint8, device=q_packed.device)
     check(_lib.load().b200_pack_w4(_p(q_packed), _p(scales), _p(zeros_x_scales), K, N, group, _p(blob), _stream()),
           "b200_pack_w4")
+    PackedWeight._write_trailer(blob, B200_FMT_INT4, K, N, group)
     return PackedWeight(B200_FMT_INT4, K, N, blob)
 
 
@@ -124,8 +152,9 @@ def pack_w8(q: torch.Tensor, col_scale: torch.Tensor) -> PackedWeight:
     n = _lib.load().b200_wo_gemm_packed_bytes(B200_FMT_INT8, K, N)
     if n == 0:
         raise B200Error(f"pack_w8: unsupported shape K={K} N={N}")
-    blob = torch.empty(int(n), dtype=torch.uint8, device=q.device)
+    blob = torch.empty(int(n) + _TRAILER_BYTES, dtype=torch.uint8, device=q.device)
     check(_lib.load().b200_pack_w8(_p(q), K, N, _p(blob), _stream()), "b200_pack_w8")
+    PackedWeight._write_trailer(blob, B200_FMT_INT8, K, N, 0)
     return PackedWeight(B200_FMT_INT8, K, N, blob, col_scale)
 
 
