@@ -27,17 +27,13 @@ except Exception:  # noqa: BLE001
         def maybe_cache_quant_scale(self, max_len: int) -> None:
             pass
 
-_WORKSPACES = {}
-
-
 def _workspace(device, max_batch, K, N):
-    key = (device, )
+    """Scratch of ONE linear module (split-K partials + semaphores), sized once at construction for its own (K, N) and the
+    largest batch a call handles: never reallocated, never shared -- safe under CUDA-graph capture and with several streams
+    (a process-wide buffer that grows on demand would leave captured graphs pointing at freed memory and let two GEMMs on
+    different streams share semaphores)."""
     need = int(ops._lib.load().b200_wo_gemm_workspace_bytes(max_batch, N, K))
-    ws = _WORKSPACES.get(key)
-    if ws is None or ws.numel() < need:
-        ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)   # process-lifetime scratch (cf. xqa.py:27-45)
-        _WORKSPACES[key] = ws
-    return ws
+    return torch.zeros(max(need, 16384), dtype=torch.uint8, device=device)
 
 
 def _quant_method(quant_config) -> str:
@@ -76,6 +72,7 @@ class B200WeightOnlyLinear(LinearBase):
             self.packed = ops.PackedWeight.from_tensor(weight)
         if self.packed.fmt == B200_FMT_INT8 and self.packed.col_scale is None:
             self.packed.col_scale = weight_scales
+        self._ws = _workspace(self.packed.data.device, self.MAX_BATCH, self.packed.K, self.packed.N)
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
         lead = input.shape[:-1]
@@ -84,7 +81,7 @@ class B200WeightOnlyLinear(LinearBase):
             x = x.contiguous()
         if self.packed.col_scale is not None and self.packed.col_scale.dtype != x.dtype:
             self.packed.col_scale = self.packed.col_scale.to(x.dtype).contiguous()   # the loader keeps INT8 scales in fp32 (device_impl.py:190)
-        ws = _workspace(x.device, self.MAX_BATCH, self.packed.K, self.packed.N)
+        ws = self._ws
         outs = []
         for i in range(0, x.shape[0], self.MAX_BATCH):   # decode batches are <= 128; larger inputs go in slabs
             outs.append(ops.wo_gemm(x[i:i + self.MAX_BATCH], self.packed, ws, bias=self.bias))

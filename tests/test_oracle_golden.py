@@ -229,3 +229,32 @@ def test_rope_ex_position_override_bias_logn_and_partial_dim():
         page, slot = block_ids[b, seq[b] // T], seq[b] % T
         np.testing.assert_allclose(pf[page, 1, 0, slot].astype(np.float32), xb[b, Hq + Hkv], atol=1e-3)
         assert np.abs(pf[page, 0, 0, slot].astype(np.float32)).sum() > 0
+
+
+@pytest.mark.parametrize("tag", ["f16_512", "f16_4096", "bf16_512", "bf16_4096"])
+def test_norm_ops_match_the_reference_cuda_kernels(golden_dir, tag):
+    """oracle_add_rmsnorm against OUTPUTS OF THE KERNELS THE REFERENCE BINDS (flashinfer rmsnorm / fused_add_rmsnorm,
+    RegisterBaseBindings.hpp:45-60), captured on a B200 by tools/make_gpu_golden.py: the stored residual must be bit-exact,
+    the normalised output may differ by one rounding step of the output type (sum-of-squares order)."""
+    g = np.load(os.path.join(golden_dir, "flashinfer_glue_ops.npz"))
+    is_bf16 = tag.startswith("bf16")
+    x, r, w = (g[f"{tag}_{k}"].view(np.uint16) for k in ("x", "res", "w"))
+    y, _ = orc.add_rmsnorm(x, None, w, 1e-6, is_bf16)
+    tol = 1.6e-2 if is_bf16 else 2e-3
+    np.testing.assert_allclose(orc.from_bits(y, is_bf16), orc.from_bits(g[f"{tag}_rmsnorm"].view(np.uint16), is_bf16), rtol=tol, atol=tol)
+    y2, r2 = orc.add_rmsnorm(x, r, w, 1e-6, is_bf16)
+    assert np.array_equal(r2, g[f"{tag}_fused_res"].view(np.uint16))
+    np.testing.assert_allclose(orc.from_bits(y2, is_bf16), orc.from_bits(g[f"{tag}_fused_y"].view(np.uint16), is_bf16), rtol=tol, atol=tol)
+    exact = (y2 == g[f"{tag}_fused_y"].view(np.uint16)).mean()
+    assert exact > 0.97, f"only {exact:.3f} of the outputs are bit-identical to flashinfer's"
+
+
+@pytest.mark.parametrize("tag", ["f16", "bf16"])
+def test_silu_and_mul_matches_the_reference_cuda_kernel(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "flashinfer_glue_ops.npz"))
+    is_bf16 = tag == "bf16"
+    y = orc.silu_and_mul(g[f"{tag}_gate_up"].view(np.uint16), is_bf16)
+    exp = g[f"{tag}_silu_and_mul"].view(np.uint16)
+    tol = 1.6e-2 if is_bf16 else 2e-3
+    np.testing.assert_allclose(orc.from_bits(y, is_bf16), orc.from_bits(exp, is_bf16), rtol=tol, atol=tol)
+    assert (y == exp).mean() > 0.97
