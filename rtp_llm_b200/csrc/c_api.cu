@@ -151,6 +151,7 @@ void attn_split(int units, int max_tiles, int* nsplit, int* tiles_per_split) {
     // (sequence, kv-head) units): a CTA has ~3 us of fixed time, streams its 32 KB tiles at min(60 GB/s -- what its 96 KB ring
     // sustains --, HBM / resident CTAs), CTAs beyond 2*SMs are back-filled (fractional waves), a split adds ~3 us of merge.
     const double slots = 2.0 * sms, hbm = 6.2e12, r_cta = 60e9, fixed = 3e-6, merge = 3e-6, tile_bytes = 32768.0;
+    const bool cluster_ok = env_int("B200_ATTN_CLUSTER", 1) != 0;
     for (int c = 1; c <= max_tiles; ++c) {
         const int ns = (max_tiles + c - 1) / c;
         if (ns > kAttnMaxSplit) continue;
@@ -158,7 +159,10 @@ void attn_split(int units, int max_tiles, int* nsplit, int* tiles_per_split) {
         const double waves = std::max(1.0, ctas / slots);   // beyond one wave CTAs are back-filled, not lock-stepped
         const double resident = ctas < slots ? ctas : slots;
         const double rate = std::min(r_cta, hbm / resident);
-        const double cost = waves * (fixed + c * tile_bytes / rate) + (ns > 1 ? merge : 0.0);
+        // merging the splits: <= 8 splits form a cluster and merge through DSMEM (~1.5 us); more go through the L2 workspace and
+        // a last-arriver loop whose cost grows with the split count (measured 26 us for 16 splits x 8 tiles, r02)
+        const double merge_cost = ns == 1 ? 0.0 : (ns <= 8 && cluster_ok ? 1.5e-6 : merge + 0.55e-6 * ns);
+        const double cost = waves * (fixed + c * tile_bytes / rate) + merge_cost;
         if (cost < best * (1.0 - 1e-6) || (std::fabs(cost - best) <= best * 1e-6 && c > best_c)) {
             best = cost;
             best_c = c;
@@ -476,7 +480,7 @@ int b200_paged_decode_attn(const void* q, int is_bf16, void* out, size_t head_nu
     const size_t sem_b = round_up(batch * kv_head_num * sizeof(int), 256);
     const size_t ml_b = round_up(batch * head_num * (size_t)p.nsplit * 2 * sizeof(float), 256);
     const size_t o_b = batch * head_num * (size_t)p.nsplit * kAttnD * sizeof(float);
-    if (p.nsplit > 1) {
+    if (p.nsplit > 8 || (p.nsplit > 1 && !env_int("B200_ATTN_CLUSTER", 1))) {
         ARG_CHECK(workspace && workspace_bytes >= sem_b + ml_b + o_b,
                   "paged_decode_attn: workspace too small (%zu < %zu)", workspace_bytes, sem_b + ml_b + o_b);
         p.sem = reinterpret_cast<int*>(workspace);
@@ -494,28 +498,44 @@ int b200_paged_decode_attn(const void* q, int is_bf16, void* out, size_t head_nu
         if (rc) return rc;
     }
     const dim3 grid(p.nsplit, (unsigned)(batch * kv_head_num), 1);
+    p.cluster_merge = (p.nsplit >= 2 && p.nsplit <= 8 && env_int("B200_ATTN_CLUSTER", 1)) ? 1 : 0;
     static bool configured_dev[16][2] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     ARG_CHECK(dev >= 0 && dev < 16, "device ordinal %d out of range", dev);
-    bool* configured = configured_dev[dev];
-    if (is_bf16) {
-        if (!configured[1]) {
-            CUDA_CHECK(cudaFuncSetAttribute(paged_decode_attn_kernel<__nv_bfloat16>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
-            configured[1] = true;
+    auto launch = [&](auto kern, bool& configured) -> cudaError_t {
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
+            if (e != cudaSuccess) return e;
+            configured = true;
         }
-        CUDA_CHECK(launch_ex(paged_decode_attn_kernel<__nv_bfloat16>, grid, dim3(kAttnThreads), kAttnSmemBytes,
-                             (cudaStream_t)stream, g_pdl.load() != 0, map, p));
-    } else {
-        if (!configured[0]) {
-            CUDA_CHECK(cudaFuncSetAttribute(paged_decode_attn_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            kAttnSmemBytes));
-            configured[0] = true;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(kAttnThreads);
+        cfg.dynamicSmemBytes = kAttnSmemBytes;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[2];
+        int na = 0;
+        if (g_pdl.load() != 0) {
+            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
         }
-        CUDA_CHECK(launch_ex(paged_decode_attn_kernel<__half>, grid, dim3(kAttnThreads), kAttnSmemBytes,
-                             (cudaStream_t)stream, g_pdl.load() != 0, map, p));
-    }
+        if (p.cluster_merge) {
+            attr[na].id = cudaLaunchAttributeClusterDimension;
+            attr[na].val.clusterDim.x = (unsigned)p.nsplit;
+            attr[na].val.clusterDim.y = 1;
+            attr[na].val.clusterDim.z = 1;
+            ++na;
+        }
+        cfg.attrs = attr;
+        cfg.numAttrs = na;
+        return cudaLaunchKernelEx(&cfg, kern, map, p);
+    };
+    if (is_bf16)
+        CUDA_CHECK(launch(paged_decode_attn_kernel<__nv_bfloat16>, configured_dev[dev][1]));
+    else
+        CUDA_CHECK(launch(paged_decode_attn_kernel<__half>, configured_dev[dev][0]));
     return launched("paged_decode_attn_kernel");
 }
 

@@ -41,6 +41,8 @@ struct AttnParams {
     float* ws_o;              // [B*Hkv][nsplit][group][D]
     float* ws_ml;             // [B*Hkv][nsplit][group][2]
     int* sem;                 // [B*Hkv], zero on entry, zero on exit
+    int cluster_merge;        // 1: the nsplit (<= 8) CTAs of a (sequence, kv head) form a thread-block cluster (nsplit,1,1) and merge
+                              //    their partial (m, l, O) through distributed shared memory; no workspace, no semaphore
 };
 
 template <typename T>
@@ -65,7 +67,8 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
     const int ntiles = (len + kAttnTile - 1) / kAttnTile;
     const int t0 = split * p.tiles_per_split;
     const int t1 = min(t0 + p.tiles_per_split, ntiles);
-    if (t0 >= t1) return;  // this split holds no tokens of this sequence (uniform for the CTA)
+    const bool empty = t0 >= t1;                 // this split holds no tokens of this sequence (uniform for the CTA)
+    if (empty && !p.cluster_merge) return;
     const int nact = (ntiles + p.tiles_per_split - 1) / p.tiles_per_split;  // CTAs that contribute to (b, kvh)
 
     if (threadIdx.x == 0) {
@@ -115,7 +118,10 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
                 }
             }
         }
-        return;  // the producer warp takes no part in the merge (named barrier 1 counts 128 threads)
+        if (!p.cluster_merge) return;  // the producer warp takes no part in the merge (named barrier 1 counts 128 threads)
+        cluster_sync_all();            // ... but every thread of the cluster passes the two cluster barriers of the DSMEM merge
+        cluster_sync_all();
+        return;
     }
 
     // ---------------------------------------------------------------------- consumers
@@ -279,18 +285,29 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
     const int d = threadIdx.x;  // 0..127: one output channel per thread
     const size_t ws_base = ((size_t)bh * p.nsplit + split) * p.group;
     T* outp = reinterpret_cast<T*>(p.out) + ((size_t)b * p.Hq + (size_t)kvh * p.group) * kAttnD;
+    // per-CTA partial of the cluster merge: [16 rows][128] fp32 + (m, l) per row, behind the per-warp staging area
+    float* part_o = l_s + kAttnConsumerWarps * 16;
+    float* part_ml = part_o + 16 * kAttnD;
     for (int r = 0; r < p.group; ++r) {
         float m = -INFINITY;
 #pragma unroll
         for (int w = 0; w < kAttnConsumerWarps; ++w) m = fmaxf(m, m_s[w * 16 + r]);
         float acc = 0.f, l = 0.f;
+        if (m != -INFINITY) {
 #pragma unroll
-        for (int w = 0; w < kAttnConsumerWarps; ++w) {
-            const float f = fast_exp2((m_s[w * 16 + r] - m) * sl2);  // -inf -> 0 (m is finite: the CTA owns >= 1 token)
-            acc = fmaf(f, o_s[((size_t)w * 16 + r) * kAttnORowStride + d], acc);
-            l = fmaf(f, l_s[w * 16 + r], l);
+            for (int w = 0; w < kAttnConsumerWarps; ++w) {
+                const float f = fast_exp2((m_s[w * 16 + r] - m) * sl2);  // -inf -> 0
+                acc = fmaf(f, o_s[((size_t)w * 16 + r) * kAttnORowStride + d], acc);
+                l = fmaf(f, l_s[w * 16 + r], l);
+            }
         }
-        if (nact == 1) {
+        if (p.cluster_merge) {
+            part_o[r * kAttnD + d] = acc;
+            if (d == 0) {
+                part_ml[r * 2 + 0] = m;
+                part_ml[r * 2 + 1] = l;
+            }
+        } else if (nact == 1) {
             outp[(size_t)r * kAttnD + d] = from_f32<T>(acc / l);
         } else {
             p.ws_o[(ws_base + r) * kAttnD + d] = acc;
@@ -299,6 +316,39 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
                 p.ws_ml[(ws_base + r) * 2 + 1] = l;
             }
         }
+    }
+    if (p.cluster_merge) {
+        // ---------------------------------------------------------------------- cross-CTA merge through DSMEM
+        // CTA `rank` of the cluster (= split) finishes the GQA rows r = rank, rank + nsplit, ...: every row is reduced by
+        // exactly one CTA in fixed split order 0..nsplit-1 (deterministic); empty splits carry m = -inf, l = 0.
+        cluster_sync_all();
+        const int S = p.nsplit;
+        const uint32_t o_addr = smem_u32(part_o), ml_addr = smem_u32(part_ml);
+        for (int r = (int)cluster_ctarank(); r < p.group; r += S) {
+            float mm[8], ll[8], oo[8];
+            float m = -INFINITY;
+#pragma unroll
+            for (int sp = 0; sp < 8; ++sp) {
+                if (sp < S) {
+                    mm[sp] = dsmem_ld_f32(dsmem_addr(ml_addr + (r * 2 + 0) * 4, sp));
+                    ll[sp] = dsmem_ld_f32(dsmem_addr(ml_addr + (r * 2 + 1) * 4, sp));
+                    oo[sp] = dsmem_ld_f32(dsmem_addr(o_addr + (r * kAttnD + d) * 4, sp));
+                    m = fmaxf(m, mm[sp]);
+                }
+            }
+            float acc = 0.f, l = 0.f;
+#pragma unroll
+            for (int sp = 0; sp < 8; ++sp) {
+                if (sp < S) {
+                    const float f = fast_exp2((mm[sp] - m) * sl2);      // -inf -> 0 (m is finite: the sequence has >= 1 token)
+                    acc = fmaf(f, oo[sp], acc);
+                    l = fmaf(f, ll[sp], l);
+                }
+            }
+            outp[(size_t)r * kAttnD + d] = from_f32<T>(acc / l);
+        }
+        cluster_sync_all();   // peers may still be reading this CTA's partial
+        return;
     }
     if (nact == 1) return;
 

@@ -59,6 +59,12 @@ ATTN_CASES = [
     ("bf16", 3, 8, 2, 64, [63, 64, 300], torch.bfloat16, None),
     ("split every tile", 3, 8, 2, 64, [63, 64, 700], torch.float16, {"B200_ATTN_TILES_PER_SPLIT": 1}),
     ("no split", 3, 8, 2, 64, [63, 64, 700], torch.float16, {"B200_ATTN_TILES_PER_SPLIT": 1000}),
+    # 2..8 splits merge through a thread-block cluster (DSMEM); short sequences leave some CTAs of the cluster without tokens
+    ("cluster merge 6 splits ragged", 3, 8, 2, 64, [63, 64, 700], torch.float16, {"B200_ATTN_TILES_PER_SPLIT": 2}),
+    ("cluster merge 8 splits g16", 2, 16, 1, 64, [500, 1], torch.float16, {"B200_ATTN_TILES_PER_SPLIT": 1}),
+    ("cluster merge 2 splits bf16 p16", 4, 8, 2, 16, [10, 20, 65, 128], torch.bfloat16, {"B200_ATTN_TILES_PER_SPLIT": 1}),
+    ("cluster merge 3 splits mha p32", 3, 4, 4, 32, [64, 65, 190], torch.float16, {"B200_ATTN_TILES_PER_SPLIT": 1}),
+    ("workspace merge (cluster off)", 3, 8, 2, 64, [63, 64, 700], torch.float16, {"B200_ATTN_TILES_PER_SPLIT": 2, "B200_ATTN_CLUSTER": 0}),
 ]
 
 
