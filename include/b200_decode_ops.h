@@ -92,6 +92,17 @@ int b200_paged_decode_attn(const void* q, int is_bf16, void* out, size_t head_nu
                            const void* kv_pool, const int32_t* page_list, const uint32_t* sequence_lengths,
                            float q_scale, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same attention with RoPE + KV append FUSED IN (what XQA does with USE_INPUT_KV + ROPE_STYLE, 3rdparty/xqa/mha.h:82-86):
+ * replaces FusedRopeKVCacheDecodeOp.forward + XQAAttnOp.forward (rtp_llm/ops/fused_rope_kvcache_op.py:202-246 then
+ * bindings/cuda/XQAAttnOp.cc:119-156) by one launch. `qkv` is the qkv GEMM output [batch][(head_num + 2 kv_head_num) * head_dim],
+ * un-rotated; q is rotated on load, the CTA that owns the tile of position sequence_lengths[b] rotates k and appends k, v to
+ * `kv_pool` before streaming it. RopeStyle::Base, NeoX pairing, same arithmetic as b200_rope_append: cache contents and attention
+ * output are bit-identical to the two-call sequence. */
+int b200_paged_decode_attn_rope(const void* qkv, int is_bf16, void* out, size_t head_num, size_t kv_head_num, size_t head_dim,
+                                size_t batch, size_t max_blocks_per_seq, size_t max_seq_len, size_t page_size, void* kv_pool,
+                                const int32_t* page_list, const uint32_t* sequence_lengths, float q_scale, float rope_base,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ weight-only GEMM */
 
 /* Load-time weight re-layout.  Replace CudaImpl.preprocess_weights_for_mixed_gemm (rtp_llm/device/device_impl.py:392-479):

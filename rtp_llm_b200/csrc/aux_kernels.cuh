@@ -209,8 +209,10 @@ __global__ void rope_append_kernel(const T* __restrict__ qkv, T* __restrict__ q_
         const float inv_freq = exp2f(-2.0f * (float)i / (float)head_dim * log2_base);
         float sn, cs;
         sincosf((float)pos * inv_freq, &sn, &cs);
-        dst[i] = from_f32<T>(x0 * cs - x1 * sn);
-        dst[i + half] = from_f32<T>(x1 * cs + x0 * sn);
+        float r0, r1;
+        rope_rotate(x0, x1, cs, sn, r0, r1);
+        dst[i] = from_f32<T>(r0);
+        dst[i + half] = from_f32<T>(r1);
     } else {
         dst[i] = src[i];
         dst[i + half] = src[i + half];
@@ -314,7 +316,8 @@ __global__ void rope_append_ex_kernel(const T* __restrict__ qkv, const T* __rest
         float x0 = load(i), x1 = load(i + rhalf);
         if (rotate) {
             const float2 cf = (cos_sin_cache && pos < cache_positions) ? cos_sin_cache[(size_t)pos * rhalf + i] : rope_coef(cfg, 2 * i, pos);
-            const float r0 = cf.x * x0 - cf.y * x1, r1 = cf.x * x1 + cf.y * x0;
+            float r0, r1;
+            rope_rotate(x0, x1, cf.x, cf.y, r0, r1);
             x0 = r0;
             x1 = r1;
         }

@@ -434,12 +434,36 @@ size_t b200_paged_decode_attn_workspace_bytes(size_t batch, size_t head_num, siz
     return sem + ml + o;
 }
 
+static int attn_impl(const void* q, const void* qkv, float rope_base, int is_bf16, void* out, size_t head_num, size_t kv_head_num,
+                     size_t head_dim, size_t batch, size_t max_blocks_per_seq, size_t max_seq_len, size_t page_size, const void* kv_pool,
+                     const int32_t* page_list, const uint32_t* sequence_lengths, float q_scale, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
 int b200_paged_decode_attn(const void* q, int is_bf16, void* out, size_t head_num, size_t kv_head_num, size_t head_dim,
                            size_t batch, size_t max_blocks_per_seq, size_t max_seq_len, size_t page_size,
                            const void* kv_pool, const int32_t* page_list, const uint32_t* sequence_lengths,
                            float q_scale, void* workspace, size_t workspace_bytes, void* stream) {
+    ARG_CHECK(q || batch == 0, "paged_decode_attn: null pointer");
+    return attn_impl(q, nullptr, 0.f, is_bf16, out, head_num, kv_head_num, head_dim, batch, max_blocks_per_seq, max_seq_len, page_size,
+                     kv_pool, page_list, sequence_lengths, q_scale, workspace, workspace_bytes, stream);
+}
+
+int b200_paged_decode_attn_rope(const void* qkv, int is_bf16, void* out, size_t head_num, size_t kv_head_num, size_t head_dim,
+                                size_t batch, size_t max_blocks_per_seq, size_t max_seq_len, size_t page_size, void* kv_pool,
+                                const int32_t* page_list, const uint32_t* sequence_lengths, float q_scale, float rope_base,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    ARG_CHECK(qkv || batch == 0, "paged_decode_attn_rope: null pointer");
+    ARG_CHECK(rope_base > 1.f, "paged_decode_attn_rope: rope_base must be > 1");
+    return attn_impl(nullptr, qkv, rope_base, is_bf16, out, head_num, kv_head_num, head_dim, batch, max_blocks_per_seq, max_seq_len,
+                     page_size, kv_pool, page_list, sequence_lengths, q_scale, workspace, workspace_bytes, stream);
+}
+
+static int attn_impl(const void* q, const void* qkv, float rope_base, int is_bf16, void* out, size_t head_num, size_t kv_head_num,
+                     size_t head_dim, size_t batch, size_t max_blocks_per_seq, size_t max_seq_len, size_t page_size, const void* kv_pool,
+                     const int32_t* page_list, const uint32_t* sequence_lengths, float q_scale, void* workspace, size_t workspace_bytes,
+                     void* stream) {
     if (batch == 0) return B200_OK;
-    ARG_CHECK(q && out && kv_pool && page_list && sequence_lengths, "paged_decode_attn: null pointer");
+    ARG_CHECK((q || qkv) && out && kv_pool && page_list && sequence_lengths, "paged_decode_attn: null pointer");
     ARG_CHECK(head_dim == (size_t)kAttnD, "paged_decode_attn: head_dim %zu unsupported (128 only)", head_dim);
     ARG_CHECK(kv_head_num > 0 && head_num % kv_head_num == 0, "paged_decode_attn: head_num %zu not a multiple of kv_head_num %zu",
               head_num, kv_head_num);
@@ -451,15 +475,18 @@ int b200_paged_decode_attn(const void* q, int is_bf16, void* out, size_t head_nu
     ARG_CHECK(max_seq_len <= max_blocks_per_seq * page_size, "paged_decode_attn: max_seq_len %zu exceeds page table capacity %zu",
               max_seq_len, max_blocks_per_seq * page_size);
     ARG_CHECK(batch * kv_head_num <= 65535, "paged_decode_attn: batch*kv_heads %zu exceeds grid limit", batch * kv_head_num);
-    ARG_CHECK(((uintptr_t)kv_pool & 15) == 0 && ((uintptr_t)q & 3) == 0, "paged_decode_attn: misaligned pointer");
+    ARG_CHECK(((uintptr_t)kv_pool & 15) == 0 && (((uintptr_t)q | (uintptr_t)qkv) & 3) == 0, "paged_decode_attn: misaligned pointer");
     if (g_rec)
         return rec_call([=](void* st) {
-            return b200_paged_decode_attn(q, is_bf16, out, head_num, kv_head_num, head_dim, batch, max_blocks_per_seq, max_seq_len,
-                                          page_size, kv_pool, page_list, sequence_lengths, q_scale, workspace, workspace_bytes, st);
+            return attn_impl(q, qkv, rope_base, is_bf16, out, head_num, kv_head_num, head_dim, batch, max_blocks_per_seq, max_seq_len,
+                             page_size, kv_pool, page_list, sequence_lengths, q_scale, workspace, workspace_bytes, st);
         });
 
     AttnParams p{};
     p.q = q;
+    p.qkv = qkv;
+    p.kv_pool_rw = const_cast<void*>(kv_pool);
+    p.log2_base = qkv ? std::log2(rope_base) : 0.f;
     p.out = out;
     p.page_list = page_list;
     p.seq_lens = reinterpret_cast<const int32_t*>(sequence_lengths);

@@ -646,8 +646,10 @@ __device__ __forceinline__ void seg_rope(const RopeParams& p, int cta, int nctas
             const float inv_freq = exp2f(-2.0f * (float)i / (float)p.head_dim * p.log2_base);
             float sn, cs;
             sincosf((float)pos * inv_freq, &sn, &cs);
-            dst[i] = from_f32<T>(x0 * cs - x1 * sn);
-            dst[i + half] = from_f32<T>(x1 * cs + x0 * sn);
+            float r0, r1;
+            rope_rotate(x0, x1, cs, sn, r0, r1);
+            dst[i] = from_f32<T>(r0);
+            dst[i + half] = from_f32<T>(r1);
         } else {
             dst[i] = from_f32<T>(x0);
             dst[i + half] = from_f32<T>(x1);

@@ -26,7 +26,7 @@ constexpr int kAttnConsumerWarps = 4;
 constexpr int kAttnThreads = (kAttnConsumerWarps + 1) * 32;
 constexpr int kAttnStageBytes = 4 * kAttnTile * 128;  // K lo/hi + V lo/hi halves, 8 KB each = 32 KB
 constexpr int kAttnORowStride = 136;   // floats; +8 banks per row -> conflict-free float2 stores
-constexpr int kAttnSmemBytes = kAttnStages * kAttnStageBytes + 1024 /*align*/ + 256 /*barriers etc*/;
+constexpr int kAttnSmemBytes = kAttnStages * kAttnStageBytes + 1024 /*align*/ + 256 /*barriers etc*/ + 512 /*rope cos/sin table*/;
 
 struct AttnParams {
     const void* q;            // [B][Hq][D]
@@ -41,6 +41,13 @@ struct AttnParams {
     float* ws_o;              // [B*Hkv][nsplit][group][D]
     float* ws_ml;             // [B*Hkv][nsplit][group][2]
     int* sem;                 // [B*Hkv], zero on entry, zero on exit
+    // fused RoPE + KV append (XQA's USE_INPUT_KV + ROPE_STYLE, 3rdparty/xqa/mha.h:82-86): when qkv != null the kernel reads the
+    // un-rotated q | k | v of the new token from the qkv GEMM output [B][(Hq+2Hkv)*D], rotates q on load, and the CTA that owns
+    // the tile of position seq_lens[b] rotates k and appends k, v to the paged cache before streaming it. Same arithmetic as
+    // rope_append_kernel (RopeStyle::Base, NeoX pairing) -> bit-identical cache contents and attention output.
+    const void* qkv;
+    void* kv_pool_rw;
+    float log2_base;
     int cluster_merge;        // 1: the nsplit (<= 8) CTAs of a (sequence, kv head) form a thread-block cluster (nsplit,1,1) and merge
                               //    their partial (m, l, O) through distributed shared memory; no workspace, no semaphore
 };
@@ -54,6 +61,7 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kAttnStages * kAttnStageBytes);
     uint64_t* empty_bar = full_bar + kAttnStages;
     int* s_flag = reinterpret_cast<int*>(empty_bar + kAttnStages);
+    float2* cs_tab = reinterpret_cast<float2*>(smem + kAttnStages * kAttnStageBytes + 256);   // fused rope: (cos, sin) of the 64 channel pairs
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.x, bh = blockIdx.y;
@@ -82,41 +90,85 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
 
     if (warp == kAttnConsumerWarps) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            tma_prefetch_desc(&kv_map);
-            const int32_t* kpl = p.page_list + (size_t)(b * 2 + 0) * p.M;
-            const int32_t* vpl = p.page_list + (size_t)(b * 2 + 1) * p.M;
-            for (int i = t0; i < t1; ++i) {
-                const int it = i - t0, s = it % kAttnStages;
-                const uint32_t ph = (it / kAttnStages) & 1;
-                // page ids first (global loads overlap the wait below)
-                int kpage[4], vpage[4], inpage[4];
-                int nbox = 0;
+        // Tile issue is split in two so that, with the fused rope, the append of the new token (all 32 lanes) overlaps the first
+        // loads in flight: lane 0 first fills the ring with tiles that cannot contain the new token, the warp appends, then
+        // lane 0 streams the rest (the token's tile is the sequence's last tile).
+        const int32_t* kpl = p.page_list + (size_t)(b * 2 + 0) * p.M;
+        const int32_t* vpl = p.page_list + (size_t)(b * 2 + 1) * p.M;
+        auto issue = [&](int i) {
+            const int it = i - t0, s = it % kAttnStages;
+            const uint32_t ph = (it / kAttnStages) & 1;
+            // page ids first (global loads overlap the wait below)
+            int kpage[4], vpage[4], inpage[4];
+            int nbox = 0;
 #pragma unroll
-                for (int bx = 0; bx < 4; ++bx) {
-                    const int tok = i * kAttnTile + bx * p.box_h;
-                    if (bx < p.boxes_per_tile && tok < len) {
-                        const int pidx = tok >> p.log2T;
-                        kpage[bx] = kpl[pidx];
-                        vpage[bx] = vpl[pidx];
-                        inpage[bx] = tok & (p.T - 1);
-                        nbox = bx + 1;
-                    }
-                }
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                uint8_t* stage = smem + s * kAttnStageBytes;
-                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(nbox * 4 * p.box_h * 128));
-#pragma unroll
-                for (int bx = 0; bx < 4; ++bx) {
-                    if (bx < nbox) {
-                        const int row_off = bx * p.box_h * 128;
-                        tma_load_4d(stage + 0 * 8192 + row_off, &kv_map, 0, inpage[bx], kvh, kpage[bx], &full_bar[s]);
-                        tma_load_4d(stage + 1 * 8192 + row_off, &kv_map, 64, inpage[bx], kvh, kpage[bx], &full_bar[s]);
-                        tma_load_4d(stage + 2 * 8192 + row_off, &kv_map, 0, inpage[bx], kvh, vpage[bx], &full_bar[s]);
-                        tma_load_4d(stage + 3 * 8192 + row_off, &kv_map, 64, inpage[bx], kvh, vpage[bx], &full_bar[s]);
-                    }
+            for (int bx = 0; bx < 4; ++bx) {
+                const int tok = i * kAttnTile + bx * p.box_h;
+                if (bx < p.boxes_per_tile && tok < len) {
+                    const int pidx = tok >> p.log2T;
+                    kpage[bx] = kpl[pidx];
+                    vpage[bx] = vpl[pidx];
+                    inpage[bx] = tok & (p.T - 1);
+                    nbox = bx + 1;
                 }
             }
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* stage = smem + s * kAttnStageBytes;
+            mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(nbox * 4 * p.box_h * 128));
+#pragma unroll
+            for (int bx = 0; bx < 4; ++bx) {
+                if (bx < nbox) {
+                    const int row_off = bx * p.box_h * 128;
+                    tma_load_4d(stage + 0 * 8192 + row_off, &kv_map, 0, inpage[bx], kvh, kpage[bx], &full_bar[s]);
+                    tma_load_4d(stage + 1 * 8192 + row_off, &kv_map, 64, inpage[bx], kvh, kpage[bx], &full_bar[s]);
+                    tma_load_4d(stage + 2 * 8192 + row_off, &kv_map, 0, inpage[bx], kvh, vpage[bx], &full_bar[s]);
+                    tma_load_4d(stage + 3 * 8192 + row_off, &kv_map, 64, inpage[bx], kvh, vpage[bx], &full_bar[s]);
+                }
+            }
+        };
+        int first_end = t1;                               // tiles [t0, first_end) are issued before the append
+        bool own = false;
+        int pos = 0;
+        if (p.qkv) {
+            pos = p.seq_lens[b];
+            own = pos < len && (pos / kAttnTile) >= t0 && (pos / kAttnTile) < t1;      // this CTA streams the new token's tile
+            if (own) first_end = min(min(t0 + kAttnStages, t1), pos / kAttnTile);
+        }
+        if (lane == 0) {
+            tma_prefetch_desc(&kv_map);
+            for (int i = t0; i < first_end; ++i) issue(i);
+        }
+        __syncwarp();
+        if (own) {
+            const T* row = reinterpret_cast<const T*>(p.qkv) + (size_t)b * (p.Hq + 2 * p.Hkv) * kAttnD;
+            const T* ksrc = row + (size_t)(p.Hq + kvh) * kAttnD;
+            const T* vsrc = row + (size_t)(p.Hq + p.Hkv + kvh) * kAttnD;
+            const size_t page_elems = (size_t)p.Hkv * p.T * kAttnD;
+            const int32_t kpage = kpl[pos >> p.log2T], vpage = vpl[pos >> p.log2T];
+            T* pool = reinterpret_cast<T*>(p.kv_pool_rw);
+            T* kdst = pool + (size_t)kpage * page_elems + ((size_t)kvh * p.T + (pos & (p.T - 1))) * kAttnD;
+            T* vdst = pool + (size_t)vpage * page_elems + ((size_t)kvh * p.T + (pos & (p.T - 1))) * kAttnD;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int i = lane + 32 * j;                        // channel pair (i, i + 64)
+                const float x0 = to_f32<T>(ksrc[i]), x1 = to_f32<T>(ksrc[i + 64]);
+                const float inv_freq = exp2f(-2.0f * (float)i / (float)kAttnD * p.log2_base);
+                float sn, cs;
+                sincosf((float)pos * inv_freq, &sn, &cs);
+                float r0, r1;
+                rope_rotate(x0, x1, cs, sn, r0, r1);
+                kdst[i] = from_f32<T>(r0);
+                kdst[i + 64] = from_f32<T>(r1);
+                vdst[i] = vsrc[i];
+                vdst[i + 64] = vsrc[i + 64];
+            }
+            __threadfence();              // every lane's stores are performed before lane 0 (after the warp barrier) ...
+            fence_proxy_async_global();   // ... issues the TMA loads of the token's tile, which read them through the async proxy
+        }
+        __syncwarp();
+        if (own && lane == 0) fence_proxy_async_global();
+        if (lane == 0) {
+            for (int i = first_end; i < t1; ++i) issue(i);
         }
         if (!p.cluster_merge) return;  // the producer warp takes no part in the merge (named barrier 1 counts 128 threads)
         cluster_sync_all();            // ... but every thread of the cluster passes the two cluster barriers of the DSMEM merge
@@ -129,7 +181,46 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
     const int qcol = (lane & 3) * 2;     // fragment column pair
     // Q fragments for the whole head dim: 8 k-steps x 4 regs. Rows >= group are zero.
     uint32_t qf[8][4];
-    {
+    if (p.qkv) {
+        // un-rotated q straight from the qkv GEMM output; the NeoX partner of column c < 64 is column c + 64 = the same
+        // register index four k-steps later, so the rotation stays inside a thread
+        const T* qbase = reinterpret_cast<const T*>(p.qkv) + ((size_t)b * (p.Hq + 2 * p.Hkv) + (size_t)kvh * p.group) * kAttnD;
+        const bool v0 = qrow < p.group, v1 = (qrow + 8) < p.group;
+        const int pos = p.seq_lens[b];
+        if (threadIdx.x < 64) {                              // one sincosf per channel pair and CTA, shared through smem
+            const float inv_freq = exp2f(-2.0f * (float)threadIdx.x / (float)kAttnD * p.log2_base);
+            float sn, cs;
+            sincosf((float)pos * inv_freq, &sn, &cs);
+            cs_tab[threadIdx.x] = make_float2(cs, sn);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int hc = 0; hc < 2; ++hc) {                 // column groups c and c + 8 of the k-step
+                const int c = kk * 16 + qcol + hc * 8;
+                const float2 t0c = cs_tab[c], t1c = cs_tab[c + 1];
+                const float cs[2] = {t0c.x, t1c.x}, sn[2] = {t0c.y, t1c.y};
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {             // fragment rows qrow and qrow + 8
+                    const bool ok = rr ? v1 : v0;
+                    uint32_t lo = 0u, hi = 0u;
+                    if (ok) {
+                        const T* src = qbase + (size_t)(qrow + 8 * rr) * kAttnD + c;
+                        const float a0 = to_f32<T>(src[0]), a1 = to_f32<T>(src[1]);          // x0 (columns c, c+1)
+                        const float b0 = to_f32<T>(src[64]), b1 = to_f32<T>(src[65]);        // x1 (columns c+64, c+65)
+                        float l0r, h0r, l1r, h1r;
+                        rope_rotate(a0, b0, cs[0], sn[0], l0r, h0r);
+                        rope_rotate(a1, b1, cs[1], sn[1], l1r, h1r);
+                        lo = pack2<T>(l0r, l1r);
+                        hi = pack2<T>(h0r, h1r);
+                    }
+                    qf[kk][hc * 2 + rr] = lo;
+                    qf[kk + 4][hc * 2 + rr] = hi;
+                }
+            }
+        }
+    } else {
         const T* qbase = reinterpret_cast<const T*>(p.q) + ((size_t)b * p.Hq + (size_t)kvh * p.group) * kAttnD;
         const bool v0 = qrow < p.group, v1 = (qrow + 8) < p.group;
 #pragma unroll

@@ -43,6 +43,9 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+__device__ __forceinline__ void fence_proxy_async_global() {
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -240,6 +243,14 @@ template <>
 __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// The rotation of one RoPE channel pair with the rounding sequence PINNED (explicit mul / fma intrinsics): every kernel that
+// rotates (rope_append, rope_append_ex, the persistent kernel's rope op, the attention kernel's fused rope) produces the same
+// bits whatever the compiler would otherwise contract.
+__device__ __forceinline__ void rope_rotate(float x0, float x1, float cs, float sn, float& r0, float& r1) {
+    r0 = __fmaf_rn(x0, cs, -__fmul_rn(x1, sn));
+    r1 = __fmaf_rn(x1, cs, __fmul_rn(x0, sn));
+}
 
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;

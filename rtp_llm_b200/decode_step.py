@@ -61,7 +61,7 @@ class DecodeStep:
 
     def __init__(self, cfg: ModelConfig, batch: int, ctx: int, device: torch.device, tp_rank: int = 0, tp_size: int = 1,
                  dtype=torch.float16, seed: int = 0, keep_reference: bool = False, ragged: bool = False,
-                 pdl: bool = False, comm=None, fuse_silu: bool = True, fuse_ar_norm: bool = True):
+                 pdl: bool = False, comm=None, fuse_silu: bool = True, fuse_ar_norm: bool = True, fuse_rope: Optional[bool] = None):
         assert cfg.head_num % tp_size == 0 and cfg.inter % tp_size == 0
         self.cfg, self.B, self.ctx, self.dev, self.dtype = cfg, batch, ctx, device, dtype
         self.tp_rank, self.tp_size, self.comm, self.pdl = tp_rank, tp_size, comm, pdl
@@ -77,6 +77,14 @@ class DecodeStep:
         self.ref: Dict[str, list] = {} if keep_reference else None
         self.fuse_silu = fuse_silu and self.inter % 64 == 0
         self.fuse_ar_norm = fuse_ar_norm
+        # RoPE + K/V append inside the attention kernel (b200_paged_decode_attn_rope): bit-identical, one launch less per layer,
+        # but measured 0.4 % SLOWER at the headline config (same box A/B, profiles/r02_fuse_rope_ab.txt): under PDL the stand-alone
+        # rope kernel hides behind its neighbours while the fused prologue sits on the attention kernel's critical path.
+        # Default off; B200_FUSE_ROPE=1 or fuse_rope=True turns it on.
+        import os
+        if fuse_rope is None:
+            fuse_rope = os.environ.get("B200_FUSE_ROPE", "0") == "1"
+        self.fuse_rope = bool(fuse_rope) and cfg.head_dim == 128
         g = torch.Generator(device="cpu").manual_seed(seed * 1000 + 17)
         H = cfg.hidden
 
@@ -257,8 +265,12 @@ class DecodeStep:
             else:
                 self._ar_norm(self.proj, L["ln1"])          # all-reduce of the previous layer's w2 output rides along
             ops.wo_gemm(self.x, L["qkv"], self.gemm_ws, out=self.qkv, pdl=self.pdl)
-            ops.rope_append(self.qkv, L["kv"], self.page_list, self.seq_lens, self.Hq, cfg.rope_base, q_out=self.q)
-            ops.paged_decode_attn(self.q, L["kv"], self.page_list, self.seq_lens, self.ctx, self.attn_ws, out=self.attn)
+            if self.fuse_rope:    # RoPE + K/V append inside the attention kernel (one launch instead of two)
+                ops.paged_decode_attn_rope(self.qkv, L["kv"], self.page_list, self.seq_lens, self.Hq, self.ctx, cfg.rope_base,
+                                           self.attn_ws, out=self.attn)
+            else:
+                ops.rope_append(self.qkv, L["kv"], self.page_list, self.seq_lens, self.Hq, cfg.rope_base, q_out=self.q)
+                ops.paged_decode_attn(self.q, L["kv"], self.page_list, self.seq_lens, self.ctx, self.attn_ws, out=self.attn)
             ops.wo_gemm(self.attn, L["o"], self.gemm_ws, out=self.proj, pdl=self.pdl)
             self._ar_norm(self.proj, L["ln2"])
             if self.fuse_silu:     # SiLU(gate)*up in the GEMM epilogue (gate/up columns interleaved at load time)

@@ -97,6 +97,22 @@ def paged_decode_attn(q: torch.Tensor, kv_cache_base: torch.Tensor, page_list: t
     return out
 
 
+def paged_decode_attn_rope(qkv: torch.Tensor, kv_cache_base: torch.Tensor, page_list: torch.Tensor, sequence_lengths: torch.Tensor,
+                           head_num: int, max_seq_len: int, rope_base: float, workspace: torch.Tensor,
+                           out: Optional[torch.Tensor] = None, q_scale: float = 1.0) -> torch.Tensor:
+    """RoPE + K/V append + paged decode attention in ONE launch: qkv [B, (Hq+2Hkv)*D] un-rotated (the qkv GEMM output);
+    kv_cache_base receives the new token's K (rotated) and V. Bit-identical to rope_append() followed by paged_decode_attn()."""
+    _cuda_contig(qkv, kv_cache_base, page_list, workspace, out)
+    P, two, Hkv, T, D = kv_cache_base.shape
+    B = qkv.shape[0]
+    if out is None:
+        out = torch.empty((B, head_num * D), dtype=qkv.dtype, device=qkv.device)
+    check(_lib.load().b200_paged_decode_attn_rope(_p(qkv), _is_bf16(qkv), _p(out), head_num, Hkv, D, B, page_list.shape[-1], max_seq_len,
+                                                  T, _p(kv_cache_base), _p(page_list), _p(sequence_lengths), q_scale, rope_base,
+                                                  _p(workspace), workspace.numel(), _stream()), "b200_paged_decode_attn_rope")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ weight-only GEMM
 _TRAILER_BYTES = 256
 _TRAILER_MAGIC = 0x42323030574F4731        # "B200WOG1"

@@ -48,9 +48,9 @@ def oracle_step(model: DecodeStep, kv_before):
     return orc.from_bits(logits, False)
 
 
-def check_tiny_step(dev, quant="int4", batch=3, ctx=40, graph=False, pdl=False, program=False) -> float:
+def check_tiny_step(dev, quant="int4", batch=3, ctx=40, graph=False, pdl=False, program=False, fuse_rope=False) -> float:
     cfg = dataclasses.replace(TINY, quant=quant)
-    model = DecodeStep(cfg, batch, ctx, dev, keep_reference=True, ragged=True, seed=1, pdl=pdl)
+    model = DecodeStep(cfg, batch, ctx, dev, keep_reference=True, ragged=True, seed=1, pdl=pdl, fuse_rope=fuse_rope)
     kv_before = [_bits(L["kv"]) for L in model.layers]
     if program:
         model.build_program()

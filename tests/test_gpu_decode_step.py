@@ -52,3 +52,8 @@ def test_program_replays_are_identical_and_match_op_by_op():
     scale = ref.float().pow(2).mean().sqrt().item()
     assert (outs[0].float() - ref.float()).abs().max().item() <= 2e-2 * scale + 2e-2
     assert m.prog.num_launches < m.prog.num_ops
+
+
+def test_tiny_decode_step_with_rope_fused_into_attention():
+    check_tiny_step(torch.device("cuda:0"), quant="int4", batch=5, ctx=70, graph=True, pdl=True, fuse_rope=True)
+    check_tiny_step(torch.device("cuda:0"), quant="int8", batch=3, ctx=40, program=True, fuse_rope=True)

@@ -82,6 +82,51 @@ def test_attention_full_size_vs_oracle(cfg):
     _run(probe.attn_vs_ref_big, name, B, Hq, Hkv, T, S, torch.float16, ragged)
 
 
+ROPE_FUSED = [
+    ("g4 p64 ragged", 4, 8, 2, 64, [1, 64, 65, 513], torch.float16, None),
+    ("g8 p16 bf16", 3, 16, 2, 16, [10, 16, 130], torch.bfloat16, None),
+    ("mha p32 cluster splits", 3, 4, 4, 32, [63, 64, 700], torch.float16, {"B200_ATTN_TILES_PER_SPLIT": 2}),
+    ("g16 workspace splits", 2, 16, 1, 64, [900, 2], torch.float16, {"B200_ATTN_TILES_PER_SPLIT": 1}),
+    ("Llama B32 S2048", 32, 32, 8, 64, [2048] * 32, torch.float16, None),
+]
+
+
+@pytest.mark.parametrize("case", ROPE_FUSED, ids=[c[0] for c in ROPE_FUSED])
+def test_attention_with_fused_rope_is_bit_identical_to_rope_then_attention(case):
+    """b200_paged_decode_attn_rope == b200_rope_append followed by b200_paged_decode_attn, bit for bit (output and cache)."""
+    name, B, Hq, Hkv, T, lens, dtype, env = case
+    old = {}
+    for k, v in (env or {}).items():
+        old[k] = os.environ.get(k)
+        os.environ[k] = str(v)
+    try:
+        dev = torch.device("cuda")
+        g = torch.Generator(device=dev).manual_seed(len(name))
+        D = 128
+        M = max((L + T - 1) // T for L in lens)
+        P = B * M + 1
+        pool1 = torch.randn(P, 2, Hkv, T, D, generator=g, device=dev).to(dtype)
+        pool2 = pool1.clone()
+        qkv = torch.randn(B, (Hq + 2 * Hkv) * D, generator=g, device=dev).to(dtype)
+        bid = (torch.randperm(P - 1, generator=g, device=dev).to(torch.int32) + 1).reshape(B, M)
+        pl = ops.convert_block_table(bid)
+        seq = torch.tensor([L - 1 for L in lens], dtype=torch.int32, device=dev)
+        max_len = max(lens)
+        ws = ops.attn_workspace(B, Hq, Hkv, max_len, dev)
+        q = ops.rope_append(qkv, pool1, pl, seq, Hq, 500000.0)
+        out1 = ops.paged_decode_attn(q, pool1, pl, seq, max_len, ws)
+        out2 = ops.paged_decode_attn_rope(qkv, pool2, pl, seq, Hq, max_len, 500000.0, ws)
+        torch.cuda.synchronize()
+        assert torch.equal(pool1, pool2), "appended K/V differ"
+        assert torch.equal(out1, out2), f"attention output differs: max {(out1.float() - out2.float()).abs().max().item()}"
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 GEMM_SMALL = [
     ("onehot", 16, 128, 128, dict(simple=True, onehot=True)),
     ("B16 K256 N256", 16, 256, 256, {}),
