@@ -137,6 +137,11 @@ int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const
  * residual may be NULL; otherwise residual += x (in place) and y = rmsnorm(residual) * gamma. hidden % 8 == 0. */
 int b200_add_rmsnorm(const void* x, void* residual, const void* gamma, void* y, int is_bf16, int rows, int hidden,
                      float eps, void* stream);
+/* Per-head RMSNorm of the q and k heads of qkv [rows][(head_num + 2 kv_head_num) * head_dim], in place (QK-norm before RoPE):
+ * invokeFusedQkRmsNorm, rtp_llm/models_py/bindings/cuda/kernels/fused_qk_rmsnorm.cu:80-150 (call site model_desc/qwen3.py:57-79).
+ * gamma / bias are [head_dim]; biases optional (both or none); head_dim % 64 == 0. */
+int b200_qk_rmsnorm(void* qkv, const void* q_gamma, const void* k_gamma, const void* q_bias, const void* k_bias, int is_bf16,
+                    int rows, int head_num, int kv_head_num, int head_dim, float eps, void* stream);
 /* silu_and_mul: y[r][c] = silu(gate_up[r][c]) * gate_up[r][inter + c]. */
 int b200_silu_and_mul(const void* gate_up, void* y, int is_bf16, int rows, int inter, void* stream);
 /* FusedRopeKVCacheDecodeOp.forward (rtp_llm/ops/fused_rope_kvcache_op.py:202-246), RopeStyle::Base, NeoX pairing:

@@ -678,3 +678,27 @@ void oracle_rope_append_ex(const h16* qkv, const h16* bias, h16* q_out, h16* kv_
         }
     }
 }
+
+
+/* Per-head RMSNorm of q and k heads, in place: rtp_llm/models_py/bindings/cuda/kernels/fused_qk_rmsnorm.cu:24-78
+ * (fp32 sum of squares over the head, val * rsqrt(mean + eps) * gamma (+ bias), rounded to the element type). */
+void oracle_qk_rmsnorm(h16* qkv, const h16* q_gamma, const h16* k_gamma, const h16* q_bias, const h16* k_bias, int is_bf16,
+                       int rows, int head_num, int kv_head_num, int head_dim, float eps) {
+    for (int r = 0; r < rows; ++r)
+        for (int h = 0; h < head_num + kv_head_num; ++h) {
+            h16* x = qkv + ((size_t)r * (head_num + 2 * kv_head_num) + h) * head_dim;
+            const h16* g = h < head_num ? q_gamma : k_gamma;
+            const h16* bb = h < head_num ? q_bias : k_bias;
+            float ss = 0.f;
+            for (int c = 0; c < head_dim; ++c) {
+                const float v = elem_to_float(x[c], is_bf16);
+                ss += v * v;
+            }
+            const float scale = 1.0f / sqrtf(ss / (float)head_dim + eps);
+            for (int c = 0; c < head_dim; ++c) {
+                float y = elem_to_float(x[c], is_bf16) * scale * elem_to_float(g[c], is_bf16);
+                if (bb) y += elem_to_float(bb[c], is_bf16);
+                x[c] = float_to_elem(y, is_bf16);
+            }
+        }
+}

@@ -348,3 +348,15 @@ def rope_cache_yarn(dim, theta, scale, max_pos, beta_slow, beta_fast, extrapolat
     t = np.arange(int(max_pos * scale), dtype=np.float32)
     freqs = np.outer(t, inv_freq).astype(np.float32)
     return (np.stack([np.cos(freqs), np.sin(freqs)], axis=-1).reshape(freqs.shape[0], -1) * np.float32(mscale)).astype(np.float32)
+
+
+def qk_rmsnorm(qkv_bits, q_gamma_bits, k_gamma_bits, head_num, kv_head_num, head_dim, eps, q_bias_bits=None, k_bias_bits=None,
+               is_bf16=False):
+    x = np.ascontiguousarray(qkv_bits, np.uint16).copy()
+    c = lambda a: None if a is None else _p(np.ascontiguousarray(a, np.uint16))
+    qg, kg = np.ascontiguousarray(q_gamma_bits, np.uint16), np.ascontiguousarray(k_gamma_bits, np.uint16)
+    qb = None if q_bias_bits is None else np.ascontiguousarray(q_bias_bits, np.uint16)
+    kb = None if k_bias_bits is None else np.ascontiguousarray(k_bias_bits, np.uint16)
+    lib().oracle_qk_rmsnorm(_p(x), _p(qg), _p(kg), None if qb is None else _p(qb), None if kb is None else _p(kb), int(is_bf16),
+                            x.shape[0], head_num, kv_head_num, head_dim, ctypes.c_float(eps))
+    return x

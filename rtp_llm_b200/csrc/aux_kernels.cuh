@@ -163,6 +163,44 @@ __global__ void add_rmsnorm_kernel(const T* __restrict__ x, T* __restrict__ resi
     }
 }
 
+// Per-head RMSNorm of the q and k heads of a qkv row, in place (Qwen3-style QK-norm before RoPE): the op
+// rtp_llm/models_py/bindings/cuda/kernels/fused_qk_rmsnorm.cu:24-78 implements (call site model_desc/qwen3.py:57-79).
+// One warp per (row, head); fp32 sum of squares; val * rsqrt(mean + eps) * gamma (+ bias), rounded to T; v heads untouched.
+template <typename T>
+__global__ void qk_rmsnorm_kernel(T* __restrict__ qkv, const T* __restrict__ q_gamma, const T* __restrict__ k_gamma,
+                                  const T* __restrict__ q_bias, const T* __restrict__ k_bias, int rows, int head_num,
+                                  int kv_head_num, int head_dim, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int warps_per_block = blockDim.x >> 5, lane = threadIdx.x & 31;
+    const int unit = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int per_row = head_num + kv_head_num;
+    if (unit >= rows * per_row) return;
+    const int r = unit / per_row, h = unit % per_row;
+    T* x = qkv + ((size_t)r * (head_num + 2 * kv_head_num) + h) * head_dim;
+    const T* gamma = h < head_num ? q_gamma : k_gamma;
+    const T* bias = h < head_num ? q_bias : k_bias;
+    float ss = 0.f;
+    for (int c = lane * 2; c < head_dim; c += 64) {
+        const float2 v = unpack2<T>(*reinterpret_cast<const uint32_t*>(x + c));
+        ss = fmaf(v.x, v.x, fmaf(v.y, v.y, ss));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float scale = rsqrtf(ss / (float)head_dim + eps);
+    for (int c = lane * 2; c < head_dim; c += 64) {
+        const float2 v = unpack2<T>(*reinterpret_cast<const uint32_t*>(x + c));
+        const float2 g = unpack2<T>(*reinterpret_cast<const uint32_t*>(gamma + c));
+        float y0 = v.x * scale * g.x, y1 = v.y * scale * g.y;
+        if (bias) {
+            const float2 bb = unpack2<T>(*reinterpret_cast<const uint32_t*>(bias + c));
+            y0 += bb.x;
+            y1 += bb.y;
+        }
+        *reinterpret_cast<uint32_t*>(x + c) = pack2<T>(y0, y1);
+    }
+}
+
 // y[r][c] = silu(gate_up[r][c]) * gate_up[r][inter + c]   (activation_kernels.cu silu_and_mul semantics)
 template <typename T>
 __global__ void silu_and_mul_kernel(const T* __restrict__ gate_up, T* __restrict__ y, int rows, int inter) {

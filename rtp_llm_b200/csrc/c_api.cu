@@ -773,6 +773,30 @@ int b200_add_rmsnorm(const void* x, void* residual, const void* gamma, void* y, 
     return launched("add_rmsnorm_kernel");
 }
 
+int b200_qk_rmsnorm(void* qkv, const void* q_gamma, const void* k_gamma, const void* q_bias, const void* k_bias, int is_bf16,
+                    int rows, int head_num, int kv_head_num, int head_dim, float eps, void* stream) {
+    if (rows == 0) return B200_OK;
+    ARG_CHECK(qkv && q_gamma && k_gamma, "qk_rmsnorm: null pointer");
+    ARG_CHECK((q_bias == nullptr) == (k_bias == nullptr), "qk_rmsnorm: give both biases or none");
+    ARG_CHECK(head_dim > 0 && head_dim % 64 == 0, "qk_rmsnorm: head_dim %d must be a multiple of 64 (fused_qk_rmsnorm.cu:104-106)", head_dim);
+    ARG_CHECK(rows > 0 && head_num > 0 && kv_head_num > 0, "qk_rmsnorm: bad shape");
+    if (g_rec)
+        return rec_call([=](void* st) {
+            return b200_qk_rmsnorm(qkv, q_gamma, k_gamma, q_bias, k_bias, is_bf16, rows, head_num, kv_head_num, head_dim, eps, st);
+        });
+    const int units = rows * (head_num + kv_head_num), wpb = 8;
+    const dim3 grid((units + wpb - 1) / wpb);
+    const bool pdl = g_pdl.load() != 0;
+    if (is_bf16)
+        CUDA_CHECK(launch_ex(qk_rmsnorm_kernel<__nv_bfloat16>, grid, dim3(wpb * 32), 0, (cudaStream_t)stream, pdl, (__nv_bfloat16*)qkv,
+                             (const __nv_bfloat16*)q_gamma, (const __nv_bfloat16*)k_gamma, (const __nv_bfloat16*)q_bias,
+                             (const __nv_bfloat16*)k_bias, rows, head_num, kv_head_num, head_dim, eps));
+    else
+        CUDA_CHECK(launch_ex(qk_rmsnorm_kernel<__half>, grid, dim3(wpb * 32), 0, (cudaStream_t)stream, pdl, (__half*)qkv, (const __half*)q_gamma,
+                             (const __half*)k_gamma, (const __half*)q_bias, (const __half*)k_bias, rows, head_num, kv_head_num, head_dim, eps));
+    return launched("qk_rmsnorm_kernel");
+}
+
 int b200_silu_and_mul(const void* gate_up, void* y, int is_bf16, int rows, int inter, void* stream) {
     if (rows == 0) return B200_OK;
     ARG_CHECK(gate_up && y, "silu_and_mul: null pointer");

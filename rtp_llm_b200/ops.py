@@ -232,6 +232,14 @@ def add_rmsnorm(x, residual, gamma, eps, out=None):
     return out
 
 
+def qk_rmsnorm(qkv, q_gamma, k_gamma, head_num, kv_head_num, head_dim, eps, q_bias=None, k_bias=None):
+    """In-place per-head RMSNorm of the q and k heads of qkv [rows, (Hq+2Hkv)*D] (fused_qk_rmsnorm.cu)."""
+    _cuda_contig(qkv, q_gamma, k_gamma, q_bias, k_bias)
+    check(_lib.load().b200_qk_rmsnorm(_p(qkv), _p(q_gamma), _p(k_gamma), _p(q_bias), _p(k_bias), _is_bf16(qkv), qkv.shape[0], head_num,
+                                      kv_head_num, head_dim, eps, _stream()), "b200_qk_rmsnorm")
+    return qkv
+
+
 def silu_and_mul(gate_up, out=None):
     _cuda_contig(gate_up, out)
     rows, two_inter = gate_up.shape

@@ -72,3 +72,23 @@ def test_rope_append_ex_base_equals_rope_append():
     q2 = ops.rope_append_ex(qkv, p2, pl, seq, Hq, RopeConfig(**dict(BASE, base=500000.0)))
     torch.cuda.synchronize()
     assert (q1.float() - q2.float()).abs().max().item() <= 4e-3 and (p1.float() - p2.float()).abs().max().item() <= 4e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+@pytest.mark.parametrize("with_bias", [False, True])
+def test_qk_rmsnorm_vs_oracle(dtype, with_bias):
+    """b200_qk_rmsnorm (Qwen3 QK-norm, fused_qk_rmsnorm.cu) against its restatement; v heads must stay untouched."""
+    is_bf16 = dtype == torch.bfloat16
+    rng = np.random.default_rng(4)
+    R, Hq, Hkv, D = 7, 8, 2, 128
+    mk = lambda *shape: torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).to(dtype)
+    qkv, qg, kg = mk(R, (Hq + 2 * Hkv) * D), 1 + 0.1 * mk(D), 1 + 0.1 * mk(D)
+    qb, kb = (0.1 * mk(D), 0.1 * mk(D)) if with_bias else (None, None)
+    bits = lambda t: None if t is None else t.contiguous().view(torch.int16).numpy().view(np.uint16)
+    exp = orc.qk_rmsnorm(bits(qkv), bits(qg), bits(kg), Hq, Hkv, D, 1e-6, bits(qb), bits(kb), is_bf16)
+    x = qkv.clone().to(dev)
+    ops.qk_rmsnorm(x, qg.to(dev), kg.to(dev), Hq, Hkv, D, 1e-6, None if qb is None else qb.to(dev), None if kb is None else kb.to(dev))
+    torch.cuda.synchronize()
+    tol = 1.6e-2 if is_bf16 else 2e-3
+    np.testing.assert_allclose(x.float().cpu().numpy(), orc.from_bits(exp, is_bf16), rtol=tol, atol=tol)
+    assert torch.equal(x[:, (Hq + Hkv) * D:].cpu(), qkv[:, (Hq + Hkv) * D:])

@@ -258,3 +258,17 @@ def test_silu_and_mul_matches_the_reference_cuda_kernel(golden_dir, tag):
     tol = 1.6e-2 if is_bf16 else 2e-3
     np.testing.assert_allclose(orc.from_bits(y, is_bf16), orc.from_bits(exp, is_bf16), rtol=tol, atol=tol)
     assert (y == exp).mean() > 0.97
+
+
+def test_qk_rmsnorm_oracle_against_numpy():
+    rng = np.random.default_rng(8)
+    R, Hq, Hkv, D = 3, 4, 2, 64
+    qkv = rng.standard_normal((R, (Hq + 2 * Hkv) * D)).astype(np.float16)
+    qg, kg = (1 + 0.1 * rng.standard_normal(D)).astype(np.float16), (1 + 0.1 * rng.standard_normal(D)).astype(np.float16)
+    out = orc.from_bits(orc.qk_rmsnorm(qkv.view(np.uint16), qg.view(np.uint16), kg.view(np.uint16), Hq, Hkv, D, 1e-6), False)
+    x = qkv.astype(np.float32).reshape(R, Hq + 2 * Hkv, D)
+    exp = x.copy()
+    for h in range(Hq + Hkv):
+        g = (qg if h < Hq else kg).astype(np.float32)
+        exp[:, h] = x[:, h] / np.sqrt((x[:, h] ** 2).mean(-1, keepdims=True) + 1e-6) * g
+    np.testing.assert_allclose(out.reshape(exp.shape), exp, rtol=2e-3, atol=2e-3)
