@@ -59,7 +59,7 @@ class B200DecodeAttnOp:
         if getattr(attn_inputs, "is_prefill", False):
             return False
         group = c.head_num // max(c.kv_head_num, 1)
-        ok = (c.size_per_head == 128 and c.head_num % max(c.kv_head_num, 1) == 0 and 1 <= group <= 16
+        ok = (c.size_per_head in (64, 128, 256) and c.head_num % max(c.kv_head_num, 1) == 0 and 1 <= group <= 16
               and _tokens_per_block(c) in (16, 32, 64, 128))
         kv_dtype = str(getattr(c, "kv_cache_dtype", "BASE"))
         return ok and "FP8" not in kv_dtype.upper() and torch.cuda.is_available() and \

@@ -142,7 +142,7 @@ size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ---- attention launch shape
 constexpr int kAttnMaxSplit = 64;
-void attn_split(int units, int max_tiles, int* nsplit, int* tiles_per_split) {
+void attn_split(int units, int max_tiles, int* nsplit, int* tiles_per_split, int head_dim = 128) {
     int forced = env_int("B200_ATTN_TILES_PER_SPLIT", 0);
     int best_c = max_tiles;
     double best = 1e30;
@@ -150,7 +150,7 @@ void attn_split(int units, int max_tiles, int* nsplit, int* tiles_per_split) {
     // Model fitted to measurements on B200 (profiles/r01_kernel_bench.txt, tools/tp8_shapes.py; within ~10 % for 32..256
     // (sequence, kv-head) units): a CTA has ~3 us of fixed time, streams its 32 KB tiles at min(60 GB/s -- what its 96 KB ring
     // sustains --, HBM / resident CTAs), CTAs beyond 2*SMs are back-filled (fractional waves), a split adds ~3 us of merge.
-    const double slots = 2.0 * sms, hbm = 6.2e12, r_cta = 60e9, fixed = 3e-6, merge = 3e-6, tile_bytes = 32768.0;
+    const double slots = 2.0 * sms, hbm = 6.2e12, r_cta = 60e9, fixed = 3e-6, merge = 3e-6, tile_bytes = 32768.0 * head_dim / 128.0;
     const bool cluster_ok = env_int("B200_ATTN_CLUSTER", 1) != 0;
     for (int c = 1; c <= max_tiles; ++c) {
         const int ns = (max_tiles + c - 1) / c;
@@ -430,7 +430,7 @@ size_t b200_paged_decode_attn_workspace_bytes(size_t batch, size_t head_num, siz
     size_t ns = tiles < (size_t)kAttnMaxSplit ? (tiles ? tiles : 1) : (size_t)kAttnMaxSplit;
     size_t sem = round_up(batch * kv_head_num * sizeof(int), 256);
     size_t ml = round_up(batch * head_num * ns * 2 * sizeof(float), 256);
-    size_t o = batch * head_num * ns * kAttnD * sizeof(float);
+    size_t o = batch * head_num * ns * 256 * sizeof(float);      // sized for the largest head_dim (256)
     return sem + ml + o;
 }
 
@@ -464,7 +464,8 @@ static int attn_impl(const void* q, const void* qkv, float rope_base, int is_bf1
                      void* stream) {
     if (batch == 0) return B200_OK;
     ARG_CHECK((q || qkv) && out && kv_pool && page_list && sequence_lengths, "paged_decode_attn: null pointer");
-    ARG_CHECK(head_dim == (size_t)kAttnD, "paged_decode_attn: head_dim %zu unsupported (128 only)", head_dim);
+    ARG_CHECK(head_dim == 64 || head_dim == 128 || head_dim == 256, "paged_decode_attn: head_dim %zu unsupported (64 / 128 / 256)", head_dim);
+    ARG_CHECK(!qkv || head_dim == 128, "paged_decode_attn_rope: the fused rope is built for head_dim 128 (got %zu)", head_dim);
     ARG_CHECK(kv_head_num > 0 && head_num % kv_head_num == 0, "paged_decode_attn: head_num %zu not a multiple of kv_head_num %zu",
               head_num, kv_head_num);
     const int group = (int)(head_num / kv_head_num);
@@ -501,12 +502,12 @@ static int attn_impl(const void* q, const void* qkv, float rope_base, int is_bf1
     p.boxes_per_tile = kAttnTile / p.box_h;
     p.scale_log2 = q_scale / std::sqrt((float)head_dim) * 1.4426950408889634f;
     const int max_tiles = (int)((max_seq_len + kAttnTile - 1) / kAttnTile);
-    attn_split((int)(batch * kv_head_num), max_tiles, &p.nsplit, &p.tiles_per_split);
+    attn_split((int)(batch * kv_head_num), max_tiles, &p.nsplit, &p.tiles_per_split, (int)head_dim);
 
     // workspace carve-up: [sem][ml][o]
     const size_t sem_b = round_up(batch * kv_head_num * sizeof(int), 256);
     const size_t ml_b = round_up(batch * head_num * (size_t)p.nsplit * 2 * sizeof(float), 256);
-    const size_t o_b = batch * head_num * (size_t)p.nsplit * kAttnD * sizeof(float);
+    const size_t o_b = batch * head_num * (size_t)p.nsplit * head_dim * sizeof(float);
     if (p.nsplit > 8 || (p.nsplit > 1 && !env_int("B200_ATTN_CLUSTER", 1))) {
         ARG_CHECK(workspace && workspace_bytes >= sem_b + ml_b + o_b,
                   "paged_decode_attn: workspace too small (%zu < %zu)", workspace_bytes, sem_b + ml_b + o_b);
@@ -517,29 +518,29 @@ static int attn_impl(const void* q, const void* qkv, float rope_base, int is_bf1
 
     CUtensorMap map;
     {
-        const cuuint64_t dims[4] = {(cuuint64_t)kAttnD, (cuuint64_t)page_size, (cuuint64_t)kv_head_num, (cuuint64_t)1 << 31};
-        const cuuint64_t strides[3] = {(cuuint64_t)kAttnD * 2, (cuuint64_t)page_size * kAttnD * 2,
-                                       (cuuint64_t)kv_head_num * page_size * kAttnD * 2};
+        const cuuint64_t dims[4] = {(cuuint64_t)head_dim, (cuuint64_t)page_size, (cuuint64_t)kv_head_num, (cuuint64_t)1 << 31};
+        const cuuint64_t strides[3] = {(cuuint64_t)head_dim * 2, (cuuint64_t)page_size * head_dim * 2,
+                                       (cuuint64_t)kv_head_num * page_size * head_dim * 2};
         const cuuint32_t box[4] = {64, (cuuint32_t)p.box_h, 1, 1};
         int rc = make_map(&map, is_bf16 != 0, 4, kv_pool, dims, strides, box);
         if (rc) return rc;
     }
     const dim3 grid(p.nsplit, (unsigned)(batch * kv_head_num), 1);
     p.cluster_merge = (p.nsplit >= 2 && p.nsplit <= 8 && env_int("B200_ATTN_CLUSTER", 1)) ? 1 : 0;
-    static bool configured_dev[16][2] = {};
+    static bool configured_dev[16][6] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     ARG_CHECK(dev >= 0 && dev < 16, "device ordinal %d out of range", dev);
-    auto launch = [&](auto kern, bool& configured) -> cudaError_t {
+    auto launch = [&](auto kern, bool& configured, int smem_bytes) -> cudaError_t {
         if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
             if (e != cudaSuccess) return e;
             configured = true;
         }
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = grid;
         cfg.blockDim = dim3(kAttnThreads);
-        cfg.dynamicSmemBytes = kAttnSmemBytes;
+        cfg.dynamicSmemBytes = smem_bytes;
         cfg.stream = (cudaStream_t)stream;
         cudaLaunchAttribute attr[2];
         int na = 0;
@@ -559,10 +560,17 @@ static int attn_impl(const void* q, const void* qkv, float rope_base, int is_bf1
         cfg.numAttrs = na;
         return cudaLaunchKernelEx(&cfg, kern, map, p);
     };
-    if (is_bf16)
-        CUDA_CHECK(launch(paged_decode_attn_kernel<__nv_bfloat16>, configured_dev[dev][1]));
-    else
-        CUDA_CHECK(launch(paged_decode_attn_kernel<__half>, configured_dev[dev][0]));
+    const int di = head_dim == 64 ? 0 : (head_dim == 128 ? 1 : 2);
+    bool& configured = configured_dev[dev][di * 2 + (is_bf16 ? 1 : 0)];
+    if (is_bf16) {
+        if (di == 0) CUDA_CHECK(launch(paged_decode_attn_kernel<__nv_bfloat16, 64>, configured, attn_smem_bytes(64)));
+        else if (di == 1) CUDA_CHECK(launch(paged_decode_attn_kernel<__nv_bfloat16, 128>, configured, attn_smem_bytes(128)));
+        else CUDA_CHECK(launch(paged_decode_attn_kernel<__nv_bfloat16, 256>, configured, attn_smem_bytes(256)));
+    } else {
+        if (di == 0) CUDA_CHECK(launch(paged_decode_attn_kernel<__half, 64>, configured, attn_smem_bytes(64)));
+        else if (di == 1) CUDA_CHECK(launch(paged_decode_attn_kernel<__half, 128>, configured, attn_smem_bytes(128)));
+        else CUDA_CHECK(launch(paged_decode_attn_kernel<__half, 256>, configured, attn_smem_bytes(256)));
+    }
     return launched("paged_decode_attn_kernel");
 }
 

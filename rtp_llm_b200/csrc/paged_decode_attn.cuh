@@ -24,9 +24,12 @@ constexpr int kAttnStages = 3;
 constexpr int kAttnD = 128;            // head dim
 constexpr int kAttnConsumerWarps = 4;
 constexpr int kAttnThreads = (kAttnConsumerWarps + 1) * 32;
-constexpr int kAttnStageBytes = 4 * kAttnTile * 128;  // K lo/hi + V lo/hi halves, 8 KB each = 32 KB
-constexpr int kAttnORowStride = 136;   // floats; +8 banks per row -> conflict-free float2 stores
-constexpr int kAttnSmemBytes = kAttnStages * kAttnStageBytes + 1024 /*align*/ + 256 /*barriers etc*/ + 512 /*rope cos/sin table*/;
+// per head dim D (64 / 128 / 256): a stage holds the D/64 64-channel halves of K, then those of V, 8 KB each (64 tokens x 128 B)
+__host__ __device__ constexpr int attn_stage_bytes(int D) { return 2 * (D / 64) * kAttnTile * 128; }
+__host__ __device__ constexpr int attn_smem_bytes(int D) {
+    return kAttnStages * attn_stage_bytes(D) + 1024 /*align*/ + 256 /*barriers etc*/ + 512 /*rope cos/sin table*/;
+}
+constexpr int kAttnSmemBytes = attn_smem_bytes(kAttnD);
 
 struct AttnParams {
     const void* q;            // [B][Hq][D]
@@ -52,16 +55,20 @@ struct AttnParams {
                               //    their partial (m, l, O) through distributed shared memory; no workspace, no semaphore
 };
 
-template <typename T>
-__global__ void __launch_bounds__(kAttnThreads, 2)
+template <typename T, int D = kAttnD>
+__global__ void __launch_bounds__(kAttnThreads, D <= 128 ? 2 : 1)
 paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnParams p) {
+    constexpr int NH = D / 64;                       // 64-channel halves per K / V row
+    constexpr int STAGE = attn_stage_bytes(D);
+    constexpr int OROW = D + 8;                      // floats; +8 banks per row -> conflict-free float2 stores
+    static_assert(D == 64 || D == 128 || D == 256, "head_dim 64 / 128 / 256");
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B-swizzled boxes
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kAttnStages * kAttnStageBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kAttnStages * STAGE);
     uint64_t* empty_bar = full_bar + kAttnStages;
     int* s_flag = reinterpret_cast<int*>(empty_bar + kAttnStages);
-    float2* cs_tab = reinterpret_cast<float2*>(smem + kAttnStages * kAttnStageBytes + 256);   // fused rope: (cos, sin) of the 64 channel pairs
+    float2* cs_tab = reinterpret_cast<float2*>(smem + kAttnStages * STAGE + 256);   // fused rope: (cos, sin) of the 64 channel pairs
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.x, bh = blockIdx.y;
@@ -113,23 +120,24 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
                 }
             }
             mbar_wait(&empty_bar[s], ph ^ 1);
-            uint8_t* stage = smem + s * kAttnStageBytes;
-            mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(nbox * 4 * p.box_h * 128));
+            uint8_t* stage = smem + s * STAGE;
+            mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(nbox * 2 * NH * p.box_h * 128));
 #pragma unroll
             for (int bx = 0; bx < 4; ++bx) {
                 if (bx < nbox) {
                     const int row_off = bx * p.box_h * 128;
-                    tma_load_4d(stage + 0 * 8192 + row_off, &kv_map, 0, inpage[bx], kvh, kpage[bx], &full_bar[s]);
-                    tma_load_4d(stage + 1 * 8192 + row_off, &kv_map, 64, inpage[bx], kvh, kpage[bx], &full_bar[s]);
-                    tma_load_4d(stage + 2 * 8192 + row_off, &kv_map, 0, inpage[bx], kvh, vpage[bx], &full_bar[s]);
-                    tma_load_4d(stage + 3 * 8192 + row_off, &kv_map, 64, inpage[bx], kvh, vpage[bx], &full_bar[s]);
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) {
+                        tma_load_4d(stage + h * 8192 + row_off, &kv_map, 64 * h, inpage[bx], kvh, kpage[bx], &full_bar[s]);
+                        tma_load_4d(stage + (NH + h) * 8192 + row_off, &kv_map, 64 * h, inpage[bx], kvh, vpage[bx], &full_bar[s]);
+                    }
                 }
             }
         };
         int first_end = t1;                               // tiles [t0, first_end) are issued before the append
         bool own = false;
         int pos = 0;
-        if (p.qkv) {
+        if (D == 128 && p.qkv != nullptr) {   // fused rope is built for head_dim 128 (the host rejects other sizes)
             pos = p.seq_lens[b];
             own = pos < len && (pos / kAttnTile) >= t0 && (pos / kAttnTile) < t1;      // this CTA streams the new token's tile
             if (own) first_end = min(min(t0 + kAttnStages, t1), pos / kAttnTile);
@@ -180,8 +188,11 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
     const int qrow = lane >> 2;          // fragment row (and row + 8)
     const int qcol = (lane & 3) * 2;     // fragment column pair
     // Q fragments for the whole head dim: 8 k-steps x 4 regs. Rows >= group are zero.
-    uint32_t qf[8][4];
-    if (p.qkv) {
+    uint32_t qf[D / 16][4];
+    bool q_loaded = false;
+    if constexpr (D == 128) {
+      if (p.qkv) {
+        q_loaded = true;
         // un-rotated q straight from the qkv GEMM output; the NeoX partner of column c < 64 is column c + 64 = the same
         // register index four k-steps later, so the rotation stays inside a thread
         const T* qbase = reinterpret_cast<const T*>(p.qkv) + ((size_t)b * (p.Hq + 2 * p.Hkv) + (size_t)kvh * p.group) * kAttnD;
@@ -220,22 +231,24 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
                 }
             }
         }
-    } else {
-        const T* qbase = reinterpret_cast<const T*>(p.q) + ((size_t)b * p.Hq + (size_t)kvh * p.group) * kAttnD;
+      }
+    }
+    if (!q_loaded) {
+        const T* qbase = reinterpret_cast<const T*>(p.q) + ((size_t)b * p.Hq + (size_t)kvh * p.group) * D;
         const bool v0 = qrow < p.group, v1 = (qrow + 8) < p.group;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
+        for (int kk = 0; kk < D / 16; ++kk) {
             const int c = kk * 16 + qcol;
-            qf[kk][0] = v0 ? *reinterpret_cast<const uint32_t*>(qbase + (size_t)qrow * kAttnD + c) : 0u;
-            qf[kk][1] = v1 ? *reinterpret_cast<const uint32_t*>(qbase + (size_t)(qrow + 8) * kAttnD + c) : 0u;
-            qf[kk][2] = v0 ? *reinterpret_cast<const uint32_t*>(qbase + (size_t)qrow * kAttnD + c + 8) : 0u;
-            qf[kk][3] = v1 ? *reinterpret_cast<const uint32_t*>(qbase + (size_t)(qrow + 8) * kAttnD + c + 8) : 0u;
+            qf[kk][0] = v0 ? *reinterpret_cast<const uint32_t*>(qbase + (size_t)qrow * D + c) : 0u;
+            qf[kk][1] = v1 ? *reinterpret_cast<const uint32_t*>(qbase + (size_t)(qrow + 8) * D + c) : 0u;
+            qf[kk][2] = v0 ? *reinterpret_cast<const uint32_t*>(qbase + (size_t)qrow * D + c + 8) : 0u;
+            qf[kk][3] = v1 ? *reinterpret_cast<const uint32_t*>(qbase + (size_t)(qrow + 8) * D + c + 8) : 0u;
         }
     }
 
-    float o[16][4];
+    float o[D / 8][4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
     float m0 = -INFINITY, m1 = -INFINITY;  // running max (raw score units) for rows qrow / qrow+8
     float l0 = 0.f, l1 = 0.f;              // per-thread partial row sums (quad-reduced at the end)
     const float sl2 = p.scale_log2;
@@ -251,8 +264,8 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
         const int it = i - t0, s = it % kAttnStages;
         const uint32_t ph = (it / kAttnStages) & 1;
         mbar_wait(&full_bar[s], ph);
-        uint8_t* stage = smem + s * kAttnStageBytes;
-        const uint32_t k_base = smem_u32(stage), v_base = k_base + 2 * 8192;
+        uint8_t* stage = smem + s * STAGE;
+        const uint32_t k_base = smem_u32(stage), v_base = k_base + NH * 8192;
 
         const int tok0 = i * kAttnTile + warp * 16;
         const int valid = len - tok0;  // tokens of this warp's slice that exist (may be <= 0)
@@ -261,9 +274,9 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
             // so the V rows are zeroed before use (K garbage is masked on the scores below).
             const int first = valid < 0 ? 0 : valid;
             for (int r = first; r < 16; ++r) {
-                uint8_t* row = stage + 2 * 8192 + (warp * 16 + r) * 128;
-                reinterpret_cast<uint32_t*>(row)[lane] = 0u;
-                reinterpret_cast<uint32_t*>(row + 8192)[lane] = 0u;
+                uint8_t* row = stage + NH * 8192 + (warp * 16 + r) * 128;
+#pragma unroll
+                for (int h = 0; h < NH; ++h) reinterpret_cast<uint32_t*>(row + h * 8192)[lane] = 0u;
             }
             __syncwarp();
         }
@@ -273,7 +286,7 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
 #pragma unroll
         for (int j = 0; j < 2; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
+        for (int kk = 0; kk < D / 16; ++kk) {
             const int half = kk >> 2, c = (kk & 3) * 2 + k_chunk_add;
             uint32_t kb[4];
             ldmatrix_x4(kb, k_base + half * 8192 + k_tokrow * 128 + ((c ^ (k_tokrow & 7)) << 4));
@@ -319,7 +332,7 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
         l1 = fmaf(l1, a1, ps1);
         if (a0 != 1.f || a1 != 1.f) {
 #pragma unroll
-            for (int n = 0; n < 16; ++n) {
+            for (int n = 0; n < D / 8; ++n) {
                 o[n][0] *= a0;
                 o[n][1] *= a0;
                 o[n][2] *= a1;
@@ -335,7 +348,7 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
 
         // ---- O += P V
 #pragma unroll
-        for (int n2 = 0; n2 < 8; ++n2) {
+        for (int n2 = 0; n2 < D / 16; ++n2) {
             const int half = n2 >> 2, c = (n2 & 3) * 2 + v_chunk_add;
             uint32_t vb[4];
             ldmatrix_x4_trans(vb, v_base + half * 8192 + v_tokrow * 128 + ((c ^ (v_tokrow & 7)) << 4));
@@ -354,15 +367,15 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
 
     // ---------------------------------------------------------------------- merge the 4 warps through smem
     asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done reading the K/V ring
-    float* o_s = reinterpret_cast<float*>(smem);                              // [4][16][kAttnORowStride]
-    float* m_s = o_s + kAttnConsumerWarps * 16 * kAttnORowStride;             // [4][16]
+    float* o_s = reinterpret_cast<float*>(smem);                              // [4][16][OROW]
+    float* m_s = o_s + kAttnConsumerWarps * 16 * OROW;                        // [4][16]
     float* l_s = m_s + kAttnConsumerWarps * 16;                               // [4][16]
     {
-        float* ow = o_s + (size_t)warp * 16 * kAttnORowStride;
+        float* ow = o_s + (size_t)warp * 16 * OROW;
 #pragma unroll
-        for (int n = 0; n < 16; ++n) {
-            *reinterpret_cast<float2*>(ow + qrow * kAttnORowStride + n * 8 + qcol) = make_float2(o[n][0], o[n][1]);
-            *reinterpret_cast<float2*>(ow + (qrow + 8) * kAttnORowStride + n * 8 + qcol) = make_float2(o[n][2], o[n][3]);
+        for (int n = 0; n < D / 8; ++n) {
+            *reinterpret_cast<float2*>(ow + qrow * OROW + n * 8 + qcol) = make_float2(o[n][0], o[n][1]);
+            *reinterpret_cast<float2*>(ow + (qrow + 8) * OROW + n * 8 + qcol) = make_float2(o[n][2], o[n][3]);
         }
         if ((lane & 3) == 0) {
             m_s[warp * 16 + qrow] = m0;
@@ -373,39 +386,43 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
 
-    const int d = threadIdx.x;  // 0..127: one output channel per thread
+    // thread t finishes the output channels t, t + 128, ... < D
+    constexpr int DPT = (D + 127) / 128;
+    const int d0 = threadIdx.x;
     const size_t ws_base = ((size_t)bh * p.nsplit + split) * p.group;
-    T* outp = reinterpret_cast<T*>(p.out) + ((size_t)b * p.Hq + (size_t)kvh * p.group) * kAttnD;
-    // per-CTA partial of the cluster merge: [16 rows][128] fp32 + (m, l) per row, behind the per-warp staging area
+    T* outp = reinterpret_cast<T*>(p.out) + ((size_t)b * p.Hq + (size_t)kvh * p.group) * D;
+    // per-CTA partial of the cluster merge: [16 rows][D] fp32 + (m, l) per row, behind the per-warp staging area
     float* part_o = l_s + kAttnConsumerWarps * 16;
-    float* part_ml = part_o + 16 * kAttnD;
+    float* part_ml = part_o + 16 * D;
     for (int r = 0; r < p.group; ++r) {
         float m = -INFINITY;
 #pragma unroll
         for (int w = 0; w < kAttnConsumerWarps; ++w) m = fmaxf(m, m_s[w * 16 + r]);
-        float acc = 0.f, l = 0.f;
-        if (m != -INFINITY) {
+        float f[kAttnConsumerWarps], l = 0.f;
 #pragma unroll
-            for (int w = 0; w < kAttnConsumerWarps; ++w) {
-                const float f = fast_exp2((m_s[w * 16 + r] - m) * sl2);  // -inf -> 0
-                acc = fmaf(f, o_s[((size_t)w * 16 + r) * kAttnORowStride + d], acc);
-                l = fmaf(f, l_s[w * 16 + r], l);
-            }
+        for (int w = 0; w < kAttnConsumerWarps; ++w) {
+            f[w] = (m == -INFINITY) ? 0.f : fast_exp2((m_s[w * 16 + r] - m) * sl2);  // -inf -> 0
+            l = fmaf(f[w], l_s[w * 16 + r], l);
         }
-        if (p.cluster_merge) {
-            part_o[r * kAttnD + d] = acc;
-            if (d == 0) {
+        if (d0 == 0) {
+            if (p.cluster_merge) {
                 part_ml[r * 2 + 0] = m;
                 part_ml[r * 2 + 1] = l;
-            }
-        } else if (nact == 1) {
-            outp[(size_t)r * kAttnD + d] = from_f32<T>(acc / l);
-        } else {
-            p.ws_o[(ws_base + r) * kAttnD + d] = acc;
-            if (d == 0) {
+            } else if (nact > 1) {
                 p.ws_ml[(ws_base + r) * 2 + 0] = m;
                 p.ws_ml[(ws_base + r) * 2 + 1] = l;
             }
+        }
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) {
+            const int d = d0 + 128 * j;
+            if (d >= D) break;
+            float acc = 0.f;
+#pragma unroll
+            for (int w = 0; w < kAttnConsumerWarps; ++w) acc = fmaf(f[w], o_s[((size_t)w * 16 + r) * OROW + d], acc);
+            if (p.cluster_merge) part_o[r * D + d] = acc;
+            else if (nact == 1) outp[(size_t)r * D + d] = from_f32<T>(acc / l);
+            else p.ws_o[(ws_base + r) * D + d] = acc;
         }
     }
     if (p.cluster_merge) {
@@ -416,27 +433,38 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
         const int S = p.nsplit;
         const uint32_t o_addr = smem_u32(part_o), ml_addr = smem_u32(part_ml);
         for (int r = (int)cluster_ctarank(); r < p.group; r += S) {
-            float mm[8], ll[8], oo[8];
+            float mm[8], ll[8];
             float m = -INFINITY;
 #pragma unroll
             for (int sp = 0; sp < 8; ++sp) {
                 if (sp < S) {
                     mm[sp] = dsmem_ld_f32(dsmem_addr(ml_addr + (r * 2 + 0) * 4, sp));
                     ll[sp] = dsmem_ld_f32(dsmem_addr(ml_addr + (r * 2 + 1) * 4, sp));
-                    oo[sp] = dsmem_ld_f32(dsmem_addr(o_addr + (r * kAttnD + d) * 4, sp));
                     m = fmaxf(m, mm[sp]);
                 }
             }
-            float acc = 0.f, l = 0.f;
+            float l = 0.f;
 #pragma unroll
             for (int sp = 0; sp < 8; ++sp) {
                 if (sp < S) {
-                    const float f = fast_exp2((mm[sp] - m) * sl2);      // -inf -> 0 (m is finite: the sequence has >= 1 token)
-                    acc = fmaf(f, oo[sp], acc);
-                    l = fmaf(f, ll[sp], l);
+                    mm[sp] = fast_exp2((mm[sp] - m) * sl2);      // -inf -> 0 (m is finite: the sequence has >= 1 token)
+                    l = fmaf(mm[sp], ll[sp], l);
                 }
             }
-            outp[(size_t)r * kAttnD + d] = from_f32<T>(acc / l);
+#pragma unroll
+            for (int j = 0; j < DPT; ++j) {
+                const int d = d0 + 128 * j;
+                if (d >= D) break;
+                float oo[8];
+#pragma unroll
+                for (int sp = 0; sp < 8; ++sp)
+                    if (sp < S) oo[sp] = dsmem_ld_f32(dsmem_addr(o_addr + (r * D + d) * 4, sp));
+                float acc = 0.f;
+#pragma unroll
+                for (int sp = 0; sp < 8; ++sp)
+                    if (sp < S) acc = fmaf(mm[sp], oo[sp], acc);
+                outp[(size_t)r * D + d] = from_f32<T>(acc / l);
+            }
         }
         cluster_sync_all();   // peers may still be reading this CTA's partial
         return;
@@ -457,14 +485,19 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
         float m = -INFINITY;
         for (int sp = 0; sp < nact; ++sp)
             m = fmaxf(m, __ldcg(&p.ws_ml[(((size_t)bh * p.nsplit + sp) * p.group + r) * 2 + 0]));
-        float acc = 0.f, l = 0.f;
-        for (int sp = 0; sp < nact; ++sp) {
-            const size_t row = ((size_t)bh * p.nsplit + sp) * p.group + r;
-            const float f = fast_exp2((__ldcg(&p.ws_ml[row * 2 + 0]) - m) * sl2);
-            acc = fmaf(f, __ldcg(&p.ws_o[row * kAttnD + d]), acc);
-            l = fmaf(f, __ldcg(&p.ws_ml[row * 2 + 1]), l);
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) {
+            const int d = d0 + 128 * j;
+            if (d >= D) break;
+            float acc = 0.f, l = 0.f;
+            for (int sp = 0; sp < nact; ++sp) {
+                const size_t row = ((size_t)bh * p.nsplit + sp) * p.group + r;
+                const float fsp = fast_exp2((__ldcg(&p.ws_ml[row * 2 + 0]) - m) * sl2);
+                acc = fmaf(fsp, __ldcg(&p.ws_o[row * D + d]), acc);
+                l = fmaf(fsp, __ldcg(&p.ws_ml[row * 2 + 1]), l);
+            }
+            outp[(size_t)r * D + d] = from_f32<T>(acc / l);
         }
-        outp[(size_t)r * kAttnD + d] = from_f32<T>(acc / l);
     }
     if (threadIdx.x == 0) p.sem[bh] = 0;  // self-reset for the next launch
 }

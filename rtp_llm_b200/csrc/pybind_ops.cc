@@ -98,7 +98,7 @@ public:
         const auto& c = attn_configs_;
         if (attn_inputs.is_prefill || c.kv_cache_fp8 || c.kv_head_num == 0 || c.head_num % c.kv_head_num) return false;
         const size_t group = c.head_num / c.kv_head_num, T = page_size_of(c);
-        if (c.size_per_head != 128 || group < 1 || group > 16) return false;
+        if ((c.size_per_head != 64 && c.size_per_head != 128 && c.size_per_head != 256) || group < 1 || group > 16) return false;
         if (!(T == 16 || T == 32 || T == 64 || T == 128)) return false;
         return b200_device_check(at::cuda::current_device()) == 0;
     }

@@ -74,6 +74,25 @@ def test_attention_vs_oracle(case):
     _run(probe.attn_vs_oracle, name, B, Hq, Hkv, T, lens, dtype, env)
 
 
+HEAD_DIMS = [
+    ("d64 g4 ragged", 64, 4, 8, 2, 64, [1, 64, 65, 513], torch.float16, None),
+    ("d64 mha p16 bf16", 64, 3, 4, 4, 16, [10, 20, 130], torch.bfloat16, None),
+    ("d64 cluster splits", 64, 3, 8, 2, 64, [63, 64, 700], torch.float16, {"B200_ATTN_TILES_PER_SPLIT": 2}),
+    ("d64 workspace splits g16", 64, 2, 16, 1, 32, [900, 2], torch.float16, {"B200_ATTN_TILES_PER_SPLIT": 1}),
+    ("d256 g4 ragged", 256, 4, 8, 2, 64, [1, 64, 65, 513], torch.float16, None),
+    ("d256 g8 p128 bf16", 256, 3, 16, 2, 128, [127, 129, 300], torch.bfloat16, None),
+    ("d256 cluster splits", 256, 3, 8, 2, 64, [63, 64, 700], torch.float16, {"B200_ATTN_TILES_PER_SPLIT": 2}),
+    ("d256 workspace splits", 256, 2, 4, 1, 16, [600, 3], torch.float16, {"B200_ATTN_TILES_PER_SPLIT": 1}),
+]
+
+
+@pytest.mark.parametrize("case", HEAD_DIMS, ids=[c[0] for c in HEAD_DIMS])
+def test_attention_head_dim_64_and_256_vs_oracle(case):
+    """The head sizes XQA ships next to 128 (3rdparty/xqa/def.bzl:49-78): same kernel, templated on head_dim."""
+    name, D, B, Hq, Hkv, T, lens, dtype, env = case
+    _run(probe.attn_vs_oracle, name, B, Hq, Hkv, T, lens, dtype, env, D=D)
+
+
 @pytest.mark.parametrize("cfg", [("Llama-3-8B B32 S2048", 32, 32, 8, 64, 2048, False),
                                  ("Llama-3-8B B32 S2048 ragged", 32, 32, 8, 64, 2048, True),
                                  ("Qwen2-72B TP8 B16 S8192", 16, 8, 1, 64, 8192, False)], ids=lambda c: c[0])

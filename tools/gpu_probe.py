@@ -49,9 +49,8 @@ def guard(name, fn):
 
 
 # ---------------------------------------------------------------------------------------------- attention
-def make_attn_case(B, Hq, Hkv, T, lens, dtype, seed=0, shuffle=True):
+def make_attn_case(B, Hq, Hkv, T, lens, dtype, seed=0, shuffle=True, D=128):
     g = torch.Generator().manual_seed(seed)
-    D = 128
     M = max(math.ceil(L / T) for L in lens)
     npages = sum(math.ceil(L / T) for L in lens) + 1
     pool = torch.randn(npages, 2, Hkv, T, D, generator=g).to(dtype)
@@ -78,19 +77,19 @@ def run_attn(q, pool, block_ids, seq, max_len=None):
     return out, ref, ws
 
 
-def attn_vs_oracle(name, B, Hq, Hkv, T, lens, dtype=torch.float16, env=None):
+def attn_vs_oracle(name, B, Hq, Hkv, T, lens, dtype=torch.float16, env=None, D=128):
     def fn():
         old = {}
         for k, v in (env or {}).items():
             old[k] = os.environ.get(k)
             os.environ[k] = str(v)
         try:
-            q, pool, block_ids, seq = make_attn_case(B, Hq, Hkv, T, lens, dtype)
+            q, pool, block_ids, seq = make_attn_case(B, Hq, Hkv, T, lens, dtype, D=D)
             out, ref, ws = run_attn(q, pool, block_ids, seq)
             is_bf16 = dtype == torch.bfloat16
             bits = lambda t: t.view(torch.int16).numpy().view(np.uint16)
             exp = orc.from_bits(orc.paged_decode_attn(bits(q), bits(pool), orc.convert_block_table(block_ids.numpy()),
-                                                      seq.numpy(), Hq, Hkv, 128, T, is_bf16=is_bf16), is_bf16)
+                                                      seq.numpy(), Hq, Hkv, D, T, is_bf16=is_bf16), is_bf16)
             tol = 2e-2 if is_bf16 else 1e-2
             ok1, i1 = diff_info(ref, exp, tol, tol)
             report(name + " [ref-kernel vs oracle]", ok1, i1)
