@@ -86,11 +86,21 @@ size_t b200_paged_decode_attn_workspace_bytes(size_t batch, size_t head_num, siz
  *                reference); attention covers positions 0..sequence_lengths[b] inclusive
  *   max_seq_len  host upper bound of sequence_lengths[b]+1 (sizes the sequence split; as XQAAttnOp.cc:149)
  *   softmax scale = q_scale * head_dim^-1/2.
- * Supported: head_dim 128, head_num/kv_head_num in 1..16, page_size in {16,32,64,128}. */
+ * Supported: head_dim 64 / 128 / 256, head_num/kv_head_num in 1..16, page_size in {16,32,64,128}. */
 int b200_paged_decode_attn(const void* q, int is_bf16, void* out, size_t head_num, size_t kv_head_num, size_t head_dim,
                            size_t batch, size_t max_blocks_per_seq, size_t max_seq_len, size_t page_size,
                            const void* kv_pool, const int32_t* page_list, const uint32_t* sequence_lengths,
                            float q_scale, void* workspace, size_t workspace_bytes, void* stream);
+
+/* q_len > 1 query tokens per sequence (verification of speculative tokens: runXqa's max_q_len, CudaXqa.h:59-84; trtllm-gen's
+ * q_len_per_req, trtllm_gen.py:544): q [batch][q_len][head_num][head_dim], out [batch][q_len][head_num*head_dim]; the K/V of all
+ * q_len new tokens are already in the cache; sequence_lengths[b] = tokens cached BEFORE them, query j attends to positions
+ * 0 .. sequence_lengths[b] + j. (head_num / kv_head_num) * q_len <= 16; max_seq_len bounds sequence_lengths[b] + q_len; size the
+ * workspace with b200_paged_decode_attn_workspace_bytes(batch * q_len, ...). q_len == 1 is b200_paged_decode_attn. */
+int b200_paged_decode_attn_multi(const void* q, int is_bf16, void* out, size_t head_num, size_t kv_head_num, size_t head_dim,
+                                 size_t batch, size_t q_len, size_t max_blocks_per_seq, size_t max_seq_len, size_t page_size,
+                                 const void* kv_pool, const int32_t* page_list, const uint32_t* sequence_lengths, float q_scale,
+                                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* The same attention with RoPE + KV append FUSED IN (what XQA does with USE_INPUT_KV + ROPE_STYLE, 3rdparty/xqa/mha.h:82-86):
  * replaces FusedRopeKVCacheDecodeOp.forward + XQAAttnOp.forward (rtp_llm/ops/fused_rope_kvcache_op.py:202-246 then

@@ -23,6 +23,8 @@ SIGNATURES = {
     "b200_paged_decode_attn_workspace_bytes": (c_size_t, [c_size_t] * 4),
     "b200_paged_decode_attn": (c_int, [c_void_p, c_int, c_void_p] + [c_size_t] * 7 + [c_void_p, c_void_p, c_void_p,
                                        c_float, c_void_p, c_size_t, c_void_p]),
+    "b200_paged_decode_attn_multi": (c_int, [c_void_p, c_int, c_void_p] + [c_size_t] * 8 + [c_void_p, c_void_p, c_void_p,
+                                             c_float, c_void_p, c_size_t, c_void_p]),
     "b200_paged_decode_attn_rope": (c_int, [c_void_p, c_int, c_void_p] + [c_size_t] * 7 + [c_void_p, c_void_p, c_void_p,
                                             c_float, c_float, c_void_p, c_size_t, c_void_p]),
     "b200_wo_gemm_packed_bytes": (c_size_t, [c_int, c_int, c_int]),

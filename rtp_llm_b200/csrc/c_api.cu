@@ -434,7 +434,7 @@ size_t b200_paged_decode_attn_workspace_bytes(size_t batch, size_t head_num, siz
     return sem + ml + o;
 }
 
-static int attn_impl(const void* q, const void* qkv, float rope_base, int is_bf16, void* out, size_t head_num, size_t kv_head_num,
+static int attn_impl(const void* q, const void* qkv, float rope_base, int q_len, int is_bf16, void* out, size_t head_num, size_t kv_head_num,
                      size_t head_dim, size_t batch, size_t max_blocks_per_seq, size_t max_seq_len, size_t page_size, const void* kv_pool,
                      const int32_t* page_list, const uint32_t* sequence_lengths, float q_scale, void* workspace, size_t workspace_bytes,
                      void* stream);
@@ -444,8 +444,18 @@ int b200_paged_decode_attn(const void* q, int is_bf16, void* out, size_t head_nu
                            const void* kv_pool, const int32_t* page_list, const uint32_t* sequence_lengths,
                            float q_scale, void* workspace, size_t workspace_bytes, void* stream) {
     ARG_CHECK(q || batch == 0, "paged_decode_attn: null pointer");
-    return attn_impl(q, nullptr, 0.f, is_bf16, out, head_num, kv_head_num, head_dim, batch, max_blocks_per_seq, max_seq_len, page_size,
+    return attn_impl(q, nullptr, 0.f, 1, is_bf16, out, head_num, kv_head_num, head_dim, batch, max_blocks_per_seq, max_seq_len, page_size,
                      kv_pool, page_list, sequence_lengths, q_scale, workspace, workspace_bytes, stream);
+}
+
+int b200_paged_decode_attn_multi(const void* q, int is_bf16, void* out, size_t head_num, size_t kv_head_num, size_t head_dim,
+                                 size_t batch, size_t q_len, size_t max_blocks_per_seq, size_t max_seq_len, size_t page_size,
+                                 const void* kv_pool, const int32_t* page_list, const uint32_t* sequence_lengths, float q_scale,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+    ARG_CHECK(q || batch == 0, "paged_decode_attn_multi: null pointer");
+    ARG_CHECK(q_len >= 1 && q_len <= 16, "paged_decode_attn_multi: q_len %zu unsupported", q_len);
+    return attn_impl(q, nullptr, 0.f, (int)q_len, is_bf16, out, head_num, kv_head_num, head_dim, batch, max_blocks_per_seq, max_seq_len,
+                     page_size, kv_pool, page_list, sequence_lengths, q_scale, workspace, workspace_bytes, stream);
 }
 
 int b200_paged_decode_attn_rope(const void* qkv, int is_bf16, void* out, size_t head_num, size_t kv_head_num, size_t head_dim,
@@ -454,11 +464,11 @@ int b200_paged_decode_attn_rope(const void* qkv, int is_bf16, void* out, size_t 
                                 void* workspace, size_t workspace_bytes, void* stream) {
     ARG_CHECK(qkv || batch == 0, "paged_decode_attn_rope: null pointer");
     ARG_CHECK(rope_base > 1.f, "paged_decode_attn_rope: rope_base must be > 1");
-    return attn_impl(nullptr, qkv, rope_base, is_bf16, out, head_num, kv_head_num, head_dim, batch, max_blocks_per_seq, max_seq_len,
+    return attn_impl(nullptr, qkv, rope_base, 1, is_bf16, out, head_num, kv_head_num, head_dim, batch, max_blocks_per_seq, max_seq_len,
                      page_size, kv_pool, page_list, sequence_lengths, q_scale, workspace, workspace_bytes, stream);
 }
 
-static int attn_impl(const void* q, const void* qkv, float rope_base, int is_bf16, void* out, size_t head_num, size_t kv_head_num,
+static int attn_impl(const void* q, const void* qkv, float rope_base, int q_len, int is_bf16, void* out, size_t head_num, size_t kv_head_num,
                      size_t head_dim, size_t batch, size_t max_blocks_per_seq, size_t max_seq_len, size_t page_size, const void* kv_pool,
                      const int32_t* page_list, const uint32_t* sequence_lengths, float q_scale, void* workspace, size_t workspace_bytes,
                      void* stream) {
@@ -470,6 +480,7 @@ static int attn_impl(const void* q, const void* qkv, float rope_base, int is_bf1
               head_num, kv_head_num);
     const int group = (int)(head_num / kv_head_num);
     ARG_CHECK(group >= 1 && group <= 16, "paged_decode_attn: group size %d unsupported (1..16)", group);
+    ARG_CHECK(group * q_len <= 16, "paged_decode_attn: group %d x q_len %d exceeds the 16 rows of one MMA tile", group, q_len);
     ARG_CHECK(page_size == 16 || page_size == 32 || page_size == 64 || page_size == 128,
               "paged_decode_attn: page_size %zu unsupported (16/32/64/128)", page_size);
     ARG_CHECK(max_seq_len >= 1, "paged_decode_attn: max_seq_len must be >= 1");
@@ -479,7 +490,7 @@ static int attn_impl(const void* q, const void* qkv, float rope_base, int is_bf1
     ARG_CHECK(((uintptr_t)kv_pool & 15) == 0 && (((uintptr_t)q | (uintptr_t)qkv) & 3) == 0, "paged_decode_attn: misaligned pointer");
     if (g_rec)
         return rec_call([=](void* st) {
-            return attn_impl(q, qkv, rope_base, is_bf16, out, head_num, kv_head_num, head_dim, batch, max_blocks_per_seq, max_seq_len,
+            return attn_impl(q, qkv, rope_base, q_len, is_bf16, out, head_num, kv_head_num, head_dim, batch, max_blocks_per_seq, max_seq_len,
                              page_size, kv_pool, page_list, sequence_lengths, q_scale, workspace, workspace_bytes, st);
         });
 
@@ -495,6 +506,7 @@ static int attn_impl(const void* q, const void* qkv, float rope_base, int is_bf1
     p.Hq = (int)head_num;
     p.Hkv = (int)kv_head_num;
     p.group = group;
+    p.q_len = q_len;
     p.M = (int)max_blocks_per_seq;
     p.T = (int)page_size;
     p.log2T = page_size == 16 ? 4 : page_size == 32 ? 5 : page_size == 64 ? 6 : 7;
@@ -506,8 +518,8 @@ static int attn_impl(const void* q, const void* qkv, float rope_base, int is_bf1
 
     // workspace carve-up: [sem][ml][o]
     const size_t sem_b = round_up(batch * kv_head_num * sizeof(int), 256);
-    const size_t ml_b = round_up(batch * head_num * (size_t)p.nsplit * 2 * sizeof(float), 256);
-    const size_t o_b = batch * head_num * (size_t)p.nsplit * head_dim * sizeof(float);
+    const size_t ml_b = round_up(batch * head_num * q_len * (size_t)p.nsplit * 2 * sizeof(float), 256);
+    const size_t o_b = batch * head_num * q_len * (size_t)p.nsplit * head_dim * sizeof(float);
     if (p.nsplit > 8 || (p.nsplit > 1 && !env_int("B200_ATTN_CLUSTER", 1))) {
         ARG_CHECK(workspace && workspace_bytes >= sem_b + ml_b + o_b,
                   "paged_decode_attn: workspace too small (%zu < %zu)", workspace_bytes, sem_b + ml_b + o_b);

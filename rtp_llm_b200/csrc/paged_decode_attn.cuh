@@ -37,6 +37,9 @@ struct AttnParams {
     const int32_t* page_list; // [B][1][2][M]
     const int32_t* seq_lens;  // [B] tokens already cached (the new token sits at this index)
     int B, Hq, Hkv, group, M;
+    int q_len;                // query tokens per sequence (1 = plain decode; > 1 = verification of speculative tokens, XQA's
+                              // max_q_len / trtllm-gen's q_len_per_req): q [B][q_len][Hq][D], query j attends to positions
+                              // 0 .. seq_lens[b] + j, its GQA rows sit at MMA rows j * group + g (group * q_len <= 16)
     int T, log2T;             // tokens per page
     int box_h, boxes_per_tile;
     int nsplit, tiles_per_split;
@@ -78,7 +81,8 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
 
     // the host sized the split for max_seq_len: a longer sequence is clamped to that bound (never more tiles than the
     // splits cover, so the last-arriver count below always matches the CTAs that really contribute)
-    const int len = min(p.seq_lens[b] + 1, p.nsplit * p.tiles_per_split * kAttnTile);
+    const int len = min(p.seq_lens[b] + p.q_len, p.nsplit * p.tiles_per_split * kAttnTile);
+    const int rows = p.group * p.q_len;
     const int ntiles = (len + kAttnTile - 1) / kAttnTile;
     const int t0 = split * p.tiles_per_split;
     const int t1 = min(t0 + p.tiles_per_split, ntiles);
@@ -234,15 +238,18 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
       }
     }
     if (!q_loaded) {
-        const T* qbase = reinterpret_cast<const T*>(p.q) + ((size_t)b * p.Hq + (size_t)kvh * p.group) * D;
-        const bool v0 = qrow < p.group, v1 = (qrow + 8) < p.group;
+        // MMA row R = j * group + g  <->  query token j, head kvh * group + g
+        const bool v0 = qrow < rows, v1 = (qrow + 8) < rows;
+        const T* qall = reinterpret_cast<const T*>(p.q);
+        const T* q0 = qall + (((size_t)b * p.q_len + qrow / p.group) * p.Hq + (size_t)kvh * p.group + qrow % p.group) * D;
+        const T* q1 = qall + (((size_t)b * p.q_len + (qrow + 8) / p.group) * p.Hq + (size_t)kvh * p.group + (qrow + 8) % p.group) * D;
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
             const int c = kk * 16 + qcol;
-            qf[kk][0] = v0 ? *reinterpret_cast<const uint32_t*>(qbase + (size_t)qrow * D + c) : 0u;
-            qf[kk][1] = v1 ? *reinterpret_cast<const uint32_t*>(qbase + (size_t)(qrow + 8) * D + c) : 0u;
-            qf[kk][2] = v0 ? *reinterpret_cast<const uint32_t*>(qbase + (size_t)qrow * D + c + 8) : 0u;
-            qf[kk][3] = v1 ? *reinterpret_cast<const uint32_t*>(qbase + (size_t)(qrow + 8) * D + c + 8) : 0u;
+            qf[kk][0] = v0 ? *reinterpret_cast<const uint32_t*>(q0 + c) : 0u;
+            qf[kk][1] = v1 ? *reinterpret_cast<const uint32_t*>(q1 + c) : 0u;
+            qf[kk][2] = v0 ? *reinterpret_cast<const uint32_t*>(q0 + c + 8) : 0u;
+            qf[kk][3] = v1 ? *reinterpret_cast<const uint32_t*>(q1 + c + 8) : 0u;
         }
     }
 
@@ -252,6 +259,7 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
     float m0 = -INFINITY, m1 = -INFINITY;  // running max (raw score units) for rows qrow / qrow+8
     float l0 = 0.f, l1 = 0.f;              // per-thread partial row sums (quad-reduced at the end)
     const float sl2 = p.scale_log2;
+    const int off0 = p.q_len - 1 - min(qrow / p.group, p.q_len - 1), off1 = p.q_len - 1 - min((qrow + 8) / p.group, p.q_len - 1);
 
     // ldmatrix lane geometry
     const int mi = lane >> 3, mr = lane & 7;
@@ -300,9 +308,10 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
         for (int j = 0; j < 2; ++j) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const bool ok = (j * 8 + qcol + e) < valid;
-                sc[j][e] = ok ? sc[j][e] : -INFINITY;
-                sc[j][2 + e] = ok ? sc[j][2 + e] : -INFINITY;
+                // query j of a q_len-token step sees q_len - 1 - j fewer tokens than the last one (causal among the new tokens)
+                const bool ok0 = (j * 8 + qcol + e) < valid - off0, ok1 = (j * 8 + qcol + e) < valid - off1;
+                sc[j][e] = ok0 ? sc[j][e] : -INFINITY;
+                sc[j][2 + e] = ok1 ? sc[j][2 + e] : -INFINITY;
                 mx0 = fmaxf(mx0, sc[j][e]);
                 mx1 = fmaxf(mx1, sc[j][2 + e]);
             }
@@ -389,12 +398,15 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
     // thread t finishes the output channels t, t + 128, ... < D
     constexpr int DPT = (D + 127) / 128;
     const int d0 = threadIdx.x;
-    const size_t ws_base = ((size_t)bh * p.nsplit + split) * p.group;
-    T* outp = reinterpret_cast<T*>(p.out) + ((size_t)b * p.Hq + (size_t)kvh * p.group) * D;
+    const size_t ws_base = ((size_t)bh * p.nsplit + split) * rows;
+    // output row of MMA row r: token r / group, head kvh * group + r % group of out [B][q_len][Hq * D]
+    auto out_row = [&](int r) {
+        return reinterpret_cast<T*>(p.out) + (((size_t)b * p.q_len + r / p.group) * p.Hq + (size_t)kvh * p.group + r % p.group) * D;
+    };
     // per-CTA partial of the cluster merge: [16 rows][D] fp32 + (m, l) per row, behind the per-warp staging area
     float* part_o = l_s + kAttnConsumerWarps * 16;
     float* part_ml = part_o + 16 * D;
-    for (int r = 0; r < p.group; ++r) {
+    for (int r = 0; r < rows; ++r) {
         float m = -INFINITY;
 #pragma unroll
         for (int w = 0; w < kAttnConsumerWarps; ++w) m = fmaxf(m, m_s[w * 16 + r]);
@@ -421,7 +433,7 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
 #pragma unroll
             for (int w = 0; w < kAttnConsumerWarps; ++w) acc = fmaf(f[w], o_s[((size_t)w * 16 + r) * OROW + d], acc);
             if (p.cluster_merge) part_o[r * D + d] = acc;
-            else if (nact == 1) outp[(size_t)r * D + d] = from_f32<T>(acc / l);
+            else if (nact == 1) out_row(r)[d] = from_f32<T>(acc / l);
             else p.ws_o[(ws_base + r) * D + d] = acc;
         }
     }
@@ -432,7 +444,7 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
         cluster_sync_all();
         const int S = p.nsplit;
         const uint32_t o_addr = smem_u32(part_o), ml_addr = smem_u32(part_ml);
-        for (int r = (int)cluster_ctarank(); r < p.group; r += S) {
+        for (int r = (int)cluster_ctarank(); r < rows; r += S) {
             float mm[8], ll[8];
             float m = -INFINITY;
 #pragma unroll
@@ -463,7 +475,7 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
 #pragma unroll
                 for (int sp = 0; sp < 8; ++sp)
                     if (sp < S) acc = fmaf(mm[sp], oo[sp], acc);
-                outp[(size_t)r * D + d] = from_f32<T>(acc / l);
+                out_row(r)[d] = from_f32<T>(acc / l);
             }
         }
         cluster_sync_all();   // peers may still be reading this CTA's partial
@@ -481,22 +493,22 @@ paged_decode_attn_kernel(const __grid_constant__ CUtensorMap kv_map, const AttnP
     asm volatile("bar.sync 1, 128;" ::: "memory");
     if (!*s_flag) return;
     __threadfence();
-    for (int r = 0; r < p.group; ++r) {
+    for (int r = 0; r < rows; ++r) {
         float m = -INFINITY;
         for (int sp = 0; sp < nact; ++sp)
-            m = fmaxf(m, __ldcg(&p.ws_ml[(((size_t)bh * p.nsplit + sp) * p.group + r) * 2 + 0]));
+            m = fmaxf(m, __ldcg(&p.ws_ml[(((size_t)bh * p.nsplit + sp) * rows + r) * 2 + 0]));
 #pragma unroll
         for (int j = 0; j < DPT; ++j) {
             const int d = d0 + 128 * j;
             if (d >= D) break;
             float acc = 0.f, l = 0.f;
             for (int sp = 0; sp < nact; ++sp) {
-                const size_t row = ((size_t)bh * p.nsplit + sp) * p.group + r;
+                const size_t row = ((size_t)bh * p.nsplit + sp) * rows + r;
                 const float fsp = fast_exp2((__ldcg(&p.ws_ml[row * 2 + 0]) - m) * sl2);
                 acc = fmaf(fsp, __ldcg(&p.ws_o[row * D + d]), acc);
                 l = fmaf(fsp, __ldcg(&p.ws_ml[row * 2 + 1]), l);
             }
-            outp[(size_t)r * D + d] = from_f32<T>(acc / l);
+            out_row(r)[d] = from_f32<T>(acc / l);
         }
     }
     if (threadIdx.x == 0) p.sem[bh] = 0;  // self-reset for the next launch

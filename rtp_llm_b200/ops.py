@@ -97,6 +97,21 @@ def paged_decode_attn(q: torch.Tensor, kv_cache_base: torch.Tensor, page_list: t
     return out
 
 
+def paged_decode_attn_multi(q: torch.Tensor, kv_cache_base: torch.Tensor, page_list: torch.Tensor, sequence_lengths: torch.Tensor,
+                            max_seq_len: int, workspace: torch.Tensor, out: Optional[torch.Tensor] = None, q_scale: float = 1.0) -> torch.Tensor:
+    """q [B, q_len, Hq, D] (q_len speculative tokens per sequence, K/V already appended); sequence_lengths [B] = tokens cached
+    before them; query j attends to positions 0 .. sequence_lengths[b] + j. Returns [B, q_len, Hq*D]."""
+    _cuda_contig(q, kv_cache_base, page_list, workspace, out)
+    P, two, Hkv, T, D = kv_cache_base.shape
+    B, q_len, Hq = q.shape[0], q.shape[1], q.shape[2]
+    if out is None:
+        out = torch.empty((B, q_len, Hq * D), dtype=q.dtype, device=q.device)
+    check(_lib.load().b200_paged_decode_attn_multi(_p(q), _is_bf16(q), _p(out), Hq, Hkv, D, B, q_len, page_list.shape[-1], max_seq_len,
+                                                   T, _p(kv_cache_base), _p(page_list), _p(sequence_lengths), q_scale,
+                                                   _p(workspace), workspace.numel(), _stream()), "b200_paged_decode_attn_multi")
+    return out
+
+
 def paged_decode_attn_rope(qkv: torch.Tensor, kv_cache_base: torch.Tensor, page_list: torch.Tensor, sequence_lengths: torch.Tensor,
                            head_num: int, max_seq_len: int, rope_base: float, workspace: torch.Tensor,
                            out: Optional[torch.Tensor] = None, q_scale: float = 1.0) -> torch.Tensor:

@@ -93,6 +93,52 @@ def test_attention_head_dim_64_and_256_vs_oracle(case):
     _run(probe.attn_vs_oracle, name, B, Hq, Hkv, T, lens, dtype, env, D=D)
 
 
+MULTI_Q = [
+    ("q_len 4 g4", 3, 4, 8, 2, 64, [10, 64, 300], torch.float16, None),
+    ("q_len 2 g8 p16 bf16", 3, 2, 16, 2, 16, [5, 17, 130], torch.bfloat16, None),
+    ("q_len 11 mha", 2, 11, 2, 2, 32, [40, 700], torch.float16, {"B200_ATTN_TILES_PER_SPLIT": 2}),
+    ("q_len 3 g4 workspace splits", 2, 3, 4, 1, 64, [900, 70], torch.float16, {"B200_ATTN_TILES_PER_SPLIT": 1}),
+    ("q_len 16 g1 crossing a tile", 1, 16, 1, 1, 64, [70], torch.float16, None),
+]
+
+
+@pytest.mark.parametrize("case", MULTI_Q, ids=[c[0] for c in MULTI_Q])
+def test_attention_with_several_query_tokens_vs_oracle(case):
+    """q_len speculative tokens per sequence (XQA max_q_len / trtllm-gen q_len_per_req): query j must equal a plain decode
+    attention over the first sequence_lengths + j + 1 positions (the oracle, one call per j)."""
+    name, B, q_len, Hq, Hkv, T, lens, dtype, env = case          # lens = tokens cached BEFORE the q_len new ones
+    old = {}
+    for k, v in (env or {}).items():
+        old[k] = os.environ.get(k)
+        os.environ[k] = str(v)
+    try:
+        dev = torch.device("cuda")
+        is_bf16 = dtype == torch.bfloat16
+        total = [L + q_len for L in lens]
+        _, pool, block_ids, _ = probe.make_attn_case(B, Hq, Hkv, T, total, dtype, seed=5)
+        g = torch.Generator().manual_seed(9)
+        q = torch.randn(B, q_len, Hq, 128, generator=g).to(dtype)
+        seq = torch.tensor(lens, dtype=torch.int32)
+        pl = ops.convert_block_table(block_ids.to(dev))
+        max_len = max(total)
+        ws = ops.attn_workspace(B * q_len, Hq, Hkv, max_len, dev)
+        out = ops.paged_decode_attn_multi(q.to(dev), pool.to(dev), pl, seq.to(dev), max_len, ws)
+        torch.cuda.synchronize()
+        bits = lambda t: t.contiguous().view(torch.int16).numpy().view(np.uint16)
+        pl_np = orc.convert_block_table(block_ids.numpy())
+        tol = 2e-2 if is_bf16 else 1e-2
+        for j in range(q_len):
+            exp = orc.from_bits(orc.paged_decode_attn(bits(q[:, j]), bits(pool), pl_np, (seq + j).numpy(), Hq, Hkv, 128, T,
+                                                      is_bf16=is_bf16), is_bf16)
+            np.testing.assert_allclose(out[:, j].float().cpu().numpy(), exp, rtol=tol, atol=tol, err_msg=f"query token {j}")
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 @pytest.mark.parametrize("cfg", [("Llama-3-8B B32 S2048", 32, 32, 8, 64, 2048, False),
                                  ("Llama-3-8B B32 S2048 ragged", 32, 32, 8, 64, 2048, True),
                                  ("Qwen2-72B TP8 B16 S8192", 16, 8, 1, 64, 8192, False)], ids=lambda c: c[0])
