@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "qwen2-72b", "tiny"])
-    ap.add_argument("--quant", default="int4", choices=["int4", "int8", "f16"])
+    ap.add_argument("--quant", default="int4", choices=["int4", "int8", "int8g", "f16"])
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--ctx", type=int, default=2048)
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("B200_PDL", "1")))  # programmatic dependent launch (bit-identical results)
@@ -99,6 +99,10 @@ def cpu_arm(args, cfg, budget_s=25.0):
         if fmt == "int4":
             w = rng.integers(0, 256, (K, Ns // 2), dtype=np.uint8)
             s = (np.abs(rng.standard_normal((K // 128, Ns), dtype=np.float32)) * 0.01 + 1e-3).astype(np.float16)
+            kw = dict(scales=s, zeros_x_scales=s, group=128)
+        elif fmt == "int8g":
+            w = rng.integers(-128, 128, (K, Ns), dtype=np.int8)
+            s = (np.abs(rng.standard_normal((K // 128, Ns), dtype=np.float32)) * 6e-4 + 6e-5).astype(np.float16)
             kw = dict(scales=s, zeros_x_scales=s, group=128)
         elif fmt == "int8":
             w = rng.integers(-128, 128, (K, Ns), dtype=np.int8)

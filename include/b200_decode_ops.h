@@ -27,6 +27,7 @@ extern "C" {
 #define B200_FMT_F16 0   /* W stored [N][K] (K contiguous), element type = activation type */
 #define B200_FMT_INT8 1  /* per-column symmetric INT8 (device_impl.py:183-222), packed by b200_pack_w8 */
 #define B200_FMT_INT4 2  /* GPTQ/AWQ group-128 INT4 (device_impl.py:242-300), packed by b200_pack_w4 */
+#define B200_FMT_INT8G 3 /* GPTQ/AWQ group-128 INT8 (device_impl.py:256-258 is_int8 branch: q_s = q_u - 128), packed by b200_pack_w8g */
 
 /* flags of b200_wo_gemm */
 #define B200_GEMM_PDL 1  /* launch with programmatic dependent launch (weights prefetched before the upstream grid ends) */
@@ -121,11 +122,15 @@ int b200_paged_decode_attn_rope(const void* qkv, int is_bf16, void* out, size_t 
  *   b200_pack_w4: q_packed uint8 [K][N/2] (low nibble = even column, two's complement q_s = q_u - 8, device_impl.py:204-209),
  *                 scales, zeros_x_scales [K/128][N] 16-bit in the ACTIVATION type (fp16 or bf16)
  *   b200_pack_w8: q int8 [K][N] (device_impl.py:183-202); the per-column scale stays a separate [N] tensor
+ *   b200_pack_w8g: q int8 [K][N] (8-bit group-wise checkpoints, q_s = q_u - 128, device_impl.py:256-274) + scales,
+ *                 zeros_x_scales [K/128][N] as for b200_pack_w4; dequant W' = q_s * s + zeros_x_scales (device_impl.py:284-291)
  * K % 128 == 0; N % 2 == 0 (int4). Output size: b200_wo_gemm_packed_bytes(fmt, K, N). */
 size_t b200_wo_gemm_packed_bytes(int fmt, int K, int N);
 int b200_pack_w4(const uint8_t* q_packed, const void* scales, const void* zeros_x_scales, int K, int N, int group,
                  void* blob, void* stream);
 int b200_pack_w8(const int8_t* q, int K, int N, void* blob, void* stream);
+int b200_pack_w8g(const int8_t* q, const void* scales, const void* zeros_x_scales, int K, int N, int group, void* blob,
+                  void* stream);
 
 /* Scratch for split-K / stream-K partials + semaphores (+ the grid-barrier words of a stand-alone call); zero-fill once
  * after allocation. Always required for INT8 / INT4 weights (at least 16 KiB). */
@@ -134,7 +139,7 @@ size_t b200_wo_gemm_workspace_bytes(int max_batch, int N, int K);
 /* Y[B][N] = X[B][K] . W' (+ bias).  The compute behind LinearBase.forward
  * (rtp_llm/models_py/modules/factory/linear/linear_base.py:81; call sites modules/hybrid/causal_attention.py:83,90,
  * dense_mlp.py:99,103; lm_head cpp/models/PyWrappedModel.cc:1041-1046) for weight-only INT4/INT8 and FP16 weights.
- *   w         B200_FMT_INT4/INT8: blob from b200_pack_w4/8; B200_FMT_F16: W [N][K] (K contiguous)
+ *   w         B200_FMT_INT4/INT8/INT8G: blob from b200_pack_w4/8/8g; B200_FMT_F16: W [N][K] (K contiguous)
  *   col_scale INT8 only: [N] per-column scale in the activation type
  *   bias      optional [N]
  * B <= 128, K % 128 == 0, x / y / w 16-byte aligned. */

@@ -282,7 +282,8 @@ static void gemm_accumulate(const float* wrow /*[N]*/, const float* xcol /*[B]*/
     }
 }
 
-/* fmt: 0 = f16/bf16 weight W[K][N]; 1 = int8 q[K][N] + scale[N]; 2 = int4 packed [K][N/2] + s,zs [K/g][N] */
+/* fmt: 0 = f16/bf16 weight W[K][N]; 1 = int8 q[K][N] + scale[N]; 2 = int4 packed [K][N/2] + s,zs [K/g][N];
+ *      3 = int8 group-wise q_s[K][N] + s,zs [K/g][N] (device_impl.py:256-258,284-291: W' = q_s*s + zeros_x_scales) */
 void oracle_dequant_gemm(const h16* x, int is_bf16, int B, int K, int N, int fmt, const void* weight,
                          const h16* scales, const h16* zeros_x_scales, int group, const h16* bias, h16* y) {
     /* column blocks so the double accumulator stays in cache and threads are independent */
@@ -302,6 +303,12 @@ void oracle_dequant_gemm(const h16* x, int is_bf16, int B, int K, int N, int fmt
                 const int8_t* w = (const int8_t*)weight + (size_t)k * N + n0;
                 for (int n = 0; n < nn; ++n)
                     wrow[n] = round_elem((float)w[n] * elem_to_float(scales[n0 + n], is_bf16), is_bf16);
+            } else if (fmt == 3) {
+                const int8_t* w = (const int8_t*)weight + (size_t)k * N + n0;
+                const h16* s = scales + (size_t)(k / group) * N + n0;
+                const h16* z = zeros_x_scales + (size_t)(k / group) * N + n0;
+                for (int n = 0; n < nn; ++n)
+                    wrow[n] = round_elem(fmaf((float)w[n], elem_to_float(s[n], is_bf16), elem_to_float(z[n], is_bf16)), is_bf16);
             } else {
                 const uint8_t* w = (const uint8_t*)weight + (size_t)k * (N / 2);
                 const h16* s = scales + (size_t)(k / group) * N;
@@ -351,6 +358,11 @@ void oracle_dequant_gemm_fast(const h16* x, int is_bf16, int B, int K, int N, in
             } else if (fmt == 1) {
                 const int8_t* w = (const int8_t*)weight + (size_t)k * N + n0;
                 for (int n = 0; n < nn; ++n) wrow[n] = (float)w[n] * elem_to_float(scales[n0 + n], is_bf16);
+            } else if (fmt == 3) {
+                const int8_t* w = (const int8_t*)weight + (size_t)k * N + n0;
+                const h16* s = scales + (size_t)(k / group) * N + n0;
+                const h16* z = zeros_x_scales + (size_t)(k / group) * N + n0;
+                for (int n = 0; n < nn; ++n) wrow[n] = (float)w[n] * elem_to_float(s[n], is_bf16) + elem_to_float(z[n], is_bf16);
             } else {
                 const uint8_t* w = (const uint8_t*)weight + (size_t)k * (N / 2) + n0 / 2;
                 const h16* s = scales + (size_t)(k / group) * N + n0;

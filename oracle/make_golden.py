@@ -121,6 +121,39 @@ def gen_quant(dev):
     print("int8", tuple(q8.shape), q8.dtype, tuple(s8.shape), s8.dtype)
 
 
+def gen_quant_w8(dev):
+    """8-bit group-wise checkpoints: the is_int8 branch of preprocess_groupwise_weight_params (device_impl.py:256-258,
+    unpack_int32_into_int16 :147-149): one byte per weight, zero shift 128, no nibble packing."""
+    g = torch.Generator().manual_seed(8)
+    K, N, group = 256, 64, 128
+    scales = (torch.randn(K // group, N, generator=g).abs() * 0.01 + 1e-3).half()
+
+    class Identity(dev.GpuImpl):
+        def __init__(self):
+            pass
+
+        @property
+        def specify_gpu_arch(self):
+            return "100"
+
+        def preprocess_weights_for_mixed_gemm(self, tensor, quant_mode, arch=""):
+            return tensor
+
+    for name, gptq, awq in (("gptq", True, False), ("awq", False, True)):
+        if gptq:
+            qweight = torch.randint(-2**31, 2**31 - 1, (K // 4, N), generator=g, dtype=torch.int64).int()
+        else:
+            qweight = torch.randint(-2**31, 2**31 - 1, (K, N // 4), generator=g, dtype=torch.int64).int()
+        qzeros = torch.randint(-2**31, 2**31 - 1, (K // group, N // 4), generator=g, dtype=torch.int64).int()
+        q8, zs, sc = Identity().preprocess_groupwise_weight_params(qweight.clone(), qzeros.clone(), scales.clone(),
+                                                                   "cpu", gptq, awq, 8)
+        assert q8.dtype == torch.int8 and tuple(q8.shape) == (K, N)
+        np.savez_compressed(os.path.join(OUT, f"quant_unpack8_{name}.npz"),
+                            qweight=qweight.numpy(), qzeros=qzeros.numpy(), scales=scales.numpy(),
+                            q=q8.numpy(), zeros_x_scales=zs.numpy(), scales_out=sc.numpy(), group=group)
+        print(name, "w8 q", tuple(q8.shape), q8.dtype, "zs", tuple(zs.shape), zs.dtype)
+
+
 def gen_attention(att):
     """Decode attention goldens through the reference's torch oracle attention_prefill_ref
     (atten_test_util.py:55-116): the decode query is placed at the last position of each sequence (other
@@ -289,8 +322,19 @@ def gen_indexing():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     dev, att = load_reference()
-    gen_quant(dev)
-    gen_attention(att)
-    gen_rope()
-    gen_rope_cache_styles()
-    gen_indexing()
+    only = set(sys.argv[1:])          # e.g. `make_golden.py quant_w8` regenerates one family; no argument = all
+
+    def want(name):
+        return not only or name in only
+    if want("quant"):
+        gen_quant(dev)
+    if want("quant_w8"):
+        gen_quant_w8(dev)
+    if want("attention"):
+        gen_attention(att)
+    if want("rope"):
+        gen_rope()
+    if want("rope_cache"):
+        gen_rope_cache_styles()
+    if want("indexing"):
+        gen_indexing()

@@ -169,6 +169,30 @@ def unpack_groupwise_int4(qweight, qzeros, scales_f16, group: int, is_gptq: bool
     return qp, zs, scales
 
 
+def unpack_groupwise_int8(qweight, qzeros, scales_f16, group: int, is_gptq: bool):
+    """device_impl.py:242-300 with weight_bits == 8 (is_int8: zero shift 128, one byte per weight, :147-149,256-258).
+    GPTQ qweight int32 [K/4, N] (4 bytes along K, low byte first), AWQ qweight int32 [K, N/4] (bytes along N, then the
+    reference applies reverse_awq_order over runs of 8 columns, :163-171,267), qzeros int32 [K/g, N/4].
+    Returns (q_s int8 [K,N], zeros_x_scales f16 [K/g,N], scales f16)."""
+    qweight = np.ascontiguousarray(qweight, dtype=np.int32)
+    qzeros = np.ascontiguousarray(qzeros, dtype=np.int32)
+    scales = np.ascontiguousarray(scales_f16, dtype=np.float16)
+
+    def awq_order(t):                       # out[..., 8g + 2j + i] = in[..., 8g + 4i + j]
+        return t.reshape(-1, 2, 4).transpose(0, 2, 1).reshape(t.shape)
+    if is_gptq:
+        u = np.ascontiguousarray(qweight.T).view(np.uint8).T.astype(np.int16)      # [K, N]
+    else:
+        u = awq_order(qweight.view(np.uint8).astype(np.int16))
+    q = (u - 128).astype(np.int8)
+    z = qzeros.view(np.uint8).astype(np.int16)
+    if not is_gptq:
+        z = awq_order(z)
+    zf = (-z + 128 - (1 if is_gptq else 0)).astype(np.float16)                      # |.| <= 128: exact in fp16
+    zs = (zf.astype(np.float32) * scales.astype(np.float32)).astype(np.float16)     # one rounding, as torch's half multiply
+    return np.ascontiguousarray(q), zs, scales
+
+
 def quantize_int8_per_col(w: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     """device_impl.py:183-202 int8 branch. w [K,N] float -> (q int8 [K,N], scale fp32 [N])."""
     w = np.ascontiguousarray(w, dtype=np.float32)
@@ -204,16 +228,21 @@ def dequant_np(fmt: str, weight, scales=None, zeros_x_scales=None, group: int = 
         s = np.repeat(np.asarray(scales, np.float32), group, axis=0)
         z = np.repeat(np.asarray(zeros_x_scales, np.float32), group, axis=0)
         return rnd(qs * s + z)
+    if fmt == "int8g":
+        s = np.repeat(np.asarray(scales, np.float32), group, axis=0)
+        z = np.repeat(np.asarray(zeros_x_scales, np.float32), group, axis=0)
+        return rnd((np.asarray(weight).astype(np.float64) * s + z).astype(np.float32))   # fma: one rounding to fp32, then to the element type
     raise ValueError(fmt)
 
 
-_FMT = {"f16": 0, "int8": 1, "int4": 2}
+_FMT = {"f16": 0, "int8": 1, "int4": 2, "int8g": 3}
 
 
 def dequant_gemm(x_bits, fmt: str, weight, scales=None, zeros_x_scales=None, group: int = 128, bias=None,
                  is_bf16=False, fast=False) -> np.ndarray:
     """Y = X . W' (+bias). x_bits [B,K] uint16; weight per fmt (f16: uint16 bits [K,N]; int8: int8 [K,N];
-    int4: uint8 [K,N/2]); scales / zeros as uint16 bits (int8: [N]; int4: [K/g,N]). Returns bits [B,N]."""
+    int4: uint8 [K,N/2]; int8g: int8 [K,N]); scales / zeros as uint16 bits (int8: [N]; int4 / int8g: [K/g,N]).
+    Returns bits [B,N]."""
     x_bits = np.ascontiguousarray(x_bits, dtype=np.uint16)
     B, K = x_bits.shape
     weight = np.ascontiguousarray(weight)

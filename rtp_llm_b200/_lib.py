@@ -6,7 +6,7 @@ from ctypes import c_char_p, c_float, c_int, c_size_t, c_uint64, c_void_p
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200_LIB_PATH") or os.path.join(HERE, "libb200_decode.so")   # override: developer A/B builds
 
-B200_FMT_F16, B200_FMT_INT8, B200_FMT_INT4 = 0, 1, 2
+B200_FMT_F16, B200_FMT_INT8, B200_FMT_INT4, B200_FMT_INT8G = 0, 1, 2, 3
 B200_GEMM_PDL = 1
 B200_GEMM_SILU_MUL = 2
 
@@ -30,6 +30,7 @@ SIGNATURES = {
     "b200_wo_gemm_packed_bytes": (c_size_t, [c_int, c_int, c_int]),
     "b200_pack_w4": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200_pack_w8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "b200_pack_w8g": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200_wo_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "b200_wo_gemm": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_size_t, c_int, c_void_p]),

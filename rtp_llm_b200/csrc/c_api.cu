@@ -592,6 +592,8 @@ size_t b200_wo_gemm_packed_bytes(int fmt, int K, int N) {
     const size_t n_tiles = (N + kGemmTileN - 1) / kGemmTileN, kb = K / kGemmBK;
     if (fmt == B200_FMT_INT4) return n_tiles * kb * kW4BlockBytes;
     if (fmt == B200_FMT_INT8) return n_tiles * kb * kW8BlockBytes;
+    if (fmt == B200_FMT_INT8G) return n_tiles * kb * kW8GBlockBytes;
+    if (fmt != B200_FMT_F16) return 0;
     return (size_t)N * K * 2;
 }
 
@@ -622,6 +624,21 @@ int b200_pack_w8(const int8_t* q, int K, int N, void* blob, void* stream) {
     return launched("pack_w8_kernel");
 }
 
+int b200_pack_w8g(const int8_t* q, const void* scales, const void* zeros_x_scales, int K, int N, int group, void* blob,
+                  void* stream) {
+    ARG_CHECK(q && scales && zeros_x_scales && blob, "pack_w8g: null pointer");
+    ARG_CHECK(group == kGemmBK, "pack_w8g: group size %d unsupported (128 only)", group);
+    ARG_CHECK(K > 0 && K % kGemmBK == 0, "pack_w8g: K=%d must be a positive multiple of 128", K);
+    ARG_CHECK(N > 0, "pack_w8g: N must be positive");
+    const size_t bytes = b200_wo_gemm_packed_bytes(B200_FMT_INT8G, K, N);
+    const int threads = 256;
+    const size_t blocks = (bytes + threads - 1) / threads;
+    pack_w8g_kernel<<<(unsigned)(blocks < 65535 ? blocks : 65535), threads, 0, (cudaStream_t)stream>>>(
+        q, reinterpret_cast<const uint16_t*>(scales), reinterpret_cast<const uint16_t*>(zeros_x_scales), K, N,
+        reinterpret_cast<uint8_t*>(blob));
+    return launched("pack_w8g_kernel");
+}
+
 size_t b200_wo_gemm_workspace_bytes(int max_batch, int N, int K) {
     if (max_batch <= 0 || N <= 0 || K <= 0 || K % kGemmBK) return 0;
     const int n_tiles = (N + kGemmTileN - 1) / kGemmTileN;
@@ -637,7 +654,8 @@ size_t b200_wo_gemm_workspace_bytes(int max_batch, int N, int K) {
 int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const void* w, const void* col_scale,
                  const void* bias, void* y, void* workspace, size_t workspace_bytes, int flags, void* stream) {
     if (B == 0) return B200_OK;
-    ARG_CHECK(fmt == B200_FMT_F16 || fmt == B200_FMT_INT8 || fmt == B200_FMT_INT4, "wo_gemm: unknown weight format %d", fmt);
+    ARG_CHECK(fmt == B200_FMT_F16 || fmt == B200_FMT_INT8 || fmt == B200_FMT_INT4 || fmt == B200_FMT_INT8G,
+              "wo_gemm: unknown weight format %d", fmt);
     ARG_CHECK(x && w && y, "wo_gemm: null pointer");
     ARG_CHECK(B > 0 && B <= 128, "wo_gemm: batch %d unsupported (1..128 per call)", B);
     ARG_CHECK(K > 0 && K % kGemmBK == 0, "wo_gemm: K=%d must be a positive multiple of 128", K);
@@ -664,7 +682,7 @@ int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const
     // (uniform split-K merged through L2). A stand-alone call uses the cluster kernel below (split-K merged through DSMEM):
     // measured on B200 at B=32 (profiles/r02_gemm_paths.txt) the cluster kernel is faster for every Llama-3-8B shape;
     // B200_GEMM_PERSISTENT=1 routes stand-alone calls through the persistent kernel too (experiments / tests).
-    const bool seg_capable = fmt != B200_FMT_F16 && bpad <= 64;
+    const bool seg_capable = (fmt == B200_FMT_INT8 || fmt == B200_FMT_INT4) && bpad <= 64;   // INT8G / FP16: cluster kernel only
     const bool streamk = seg_capable && (recording_fused(kOpGemm) || env_int("B200_GEMM_PERSISTENT", 0));
     if (streamk) {
         ARG_CHECK(workspace && workspace_bytes >= kGemmSemBytes, "wo_gemm: workspace of at least %zu bytes required", kGemmSemBytes);

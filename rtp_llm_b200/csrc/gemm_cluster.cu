@@ -60,6 +60,7 @@ int by_fmt(int fmt, int bpad, const CUtensorMap& xmap, const CUtensorMap& wmap, 
     switch (fmt) {
         case B200_FMT_F16: return by_bpad<kFmtF16, T>(bpad, xmap, wmap, p, n_tiles, st);
         case B200_FMT_INT8: return by_bpad<kFmtInt8, T>(bpad, xmap, wmap, p, n_tiles, st);
+        case B200_FMT_INT8G: return by_bpad<kFmtInt8G, T>(bpad, xmap, wmap, p, n_tiles, st);
         default: return by_bpad<kFmtInt4, T>(bpad, xmap, wmap, p, n_tiles, st);
     }
 }

@@ -1,4 +1,4 @@
-// Weight-only (INT4 group-128 / INT8 per-column / FP16) x FP16|BF16 GEMM for decode batches, sm_100a.
+// Weight-only (INT4 group-128 / INT8 per-column / INT8 group-128 / FP16) x FP16|BF16 GEMM for decode batches, sm_100a.
 //
 //   Y[b][n] = sum_k X[b][k] * W'[k][n] (+ bias[n]),   W' per /root/reference/rtp_llm/device/device_impl.py:183-222,242-300
 //   (SURVEY.md section 8 a8-a10).  Replaces the cutlass fpA_intB "mixed gemm" the reference loader still prepares weights
@@ -25,16 +25,17 @@
 
 namespace b200 {
 
-enum : int { kFmtF16 = 0, kFmtInt8 = 1, kFmtInt4 = 2 };
+enum : int { kFmtF16 = 0, kFmtInt8 = 1, kFmtInt4 = 2, kFmtInt8G = 3 };   // Int8G: 8-bit GPTQ/AWQ, group 128 (device_impl.py:256-258)
 
 constexpr int kGemmBK = 128;       // k elements per pipeline stage (= one INT4 quantisation group)
 constexpr int kGemmTileN = 128;    // output features per CTA (MMA M)
 constexpr int kW4BlockBytes = 8192 + 256 + 256;
 constexpr int kW8BlockBytes = 16384;
+constexpr int kW8GBlockBytes = 16384 + 256 + 256;   // + the group's scales and zero*scale, like the INT4 blob
 constexpr int kW16BlockBytes = 32768;
 
 __host__ __device__ constexpr int gemm_w_bytes(int fmt) {
-    return fmt == kFmtInt4 ? kW4BlockBytes : (fmt == kFmtInt8 ? kW8BlockBytes : kW16BlockBytes);
+    return fmt == kFmtInt4 ? kW4BlockBytes : (fmt == kFmtInt8 ? kW8BlockBytes : (fmt == kFmtInt8G ? kW8GBlockBytes : kW16BlockBytes));
 }
 // Shared-memory rings.  The weight ring (HBM stream) and the activation ring (L2 hits) are SEPARATE: a weight stage is
 // released as soon as the dequant warps hold its nibbles in registers, so its lifetime is one TMA latency, not the
@@ -415,9 +416,10 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
                 if (threadIdx.x == 0) B200_TRACE(2, it);
                 const uint32_t wb = smem_u32(wring) + s * W_BYTES;   // 32-bit shared address of this stage
                 typename Pair<T>::type s2, zs2;
-                if (FMT == kFmtInt4) {
-                    s2 = Pair<T>::bcast((uint16_t)lds_u16(wb + 8192 + row * 2));
-                    zs2 = Pair<T>::bcast((uint16_t)lds_u16(wb + 8192 + 256 + row * 2));
+                if (FMT == kFmtInt4 || FMT == kFmtInt8G) {
+                    constexpr int Q_BYTES = FMT == kFmtInt4 ? 8192 : 16384;
+                    s2 = Pair<T>::bcast((uint16_t)lds_u16(wb + Q_BYTES + row * 2));
+                    zs2 = Pair<T>::bcast((uint16_t)lds_u16(wb + Q_BYTES + 256 + row * 2));
                 }
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -461,6 +463,16 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
                                 Dequant8<T>::word(v[cc][h].z, &regs[cc][h * 8 + 4]);
                                 Dequant8<T>::word(v[cc][h].w, &regs[cc][h * 8 + 6]);
                             }
+                        if (FMT == kFmtInt8G) {   // group-wise 8-bit: W' = q_s * s + zero*scale, one rounding (as INT4)
+#pragma unroll
+                            for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) {
+                                    typename Pair<T>::type h = *reinterpret_cast<typename Pair<T>::type*>(&regs[cc][q]);
+                                    h = __hfma2(h, s2, zs2);
+                                    regs[cc][q] = *reinterpret_cast<uint32_t*>(&h);
+                                }
+                        }
                     }
                     if (half == 0) {
                         if (threadIdx.x == 0) B200_TRACE(3, it);
@@ -739,6 +751,30 @@ static __global__ void pack_w8_kernel(const int8_t* __restrict__ q, int K, int N
         const int c = byte_in_block / 2048, r = (byte_in_block % 2048) / 16, i = byte_in_block % 16;
         const int n = tile * kGemmTileN + r, k = kb * kGemmBK + c * 16 + i;
         blob[idx] = (n < N) ? (uint8_t)((int)q[(size_t)k * N + n] + 128) : (uint8_t)128;
+    }
+}
+
+// int8 group-wise: q [K][N] int8 (q_s = q_u - 128), scales / zs [K/128][N] (16-bit) -> blobs of u = q_s + 128 + the group's scales, zs
+static __global__ void pack_w8g_kernel(const int8_t* __restrict__ q, const uint16_t* __restrict__ scales,
+                                       const uint16_t* __restrict__ zs, int K, int N, uint8_t* __restrict__ blob) {
+    const int k_blocks = K / kGemmBK;
+    const int n_tiles = (N + kGemmTileN - 1) / kGemmTileN;
+    const size_t total = (size_t)n_tiles * k_blocks * kW8GBlockBytes;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int byte_in_block = (int)(idx % kW8GBlockBytes);
+        const size_t blk = idx / kW8GBlockBytes;
+        const int kb = (int)(blk % k_blocks), tile = (int)(blk / k_blocks);
+        if (byte_in_block < 16384) {
+            const int c = byte_in_block / 2048, r = (byte_in_block % 2048) / 16, i = byte_in_block % 16;
+            const int n = tile * kGemmTileN + r, k = kb * kGemmBK + c * 16 + i;
+            blob[idx] = (n < N) ? (uint8_t)((int)q[(size_t)k * N + n] + 128) : (uint8_t)128;
+        } else {
+            const int w = byte_in_block - 16384;         // 256 bytes of scales then 256 bytes of zs
+            const uint16_t* src = (w < 256) ? scales : zs;
+            const int r = (w % 256) / 2, n = tile * kGemmTileN + r;
+            const uint16_t v = n < N ? src[(size_t)kb * N + n] : (uint16_t)0;
+            blob[idx] = (uint8_t)((w & 1) ? (v >> 8) : (v & 0xFF));
+        }
     }
 }
 

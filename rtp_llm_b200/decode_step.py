@@ -17,7 +17,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
-from ._lib import B200_FMT_F16, B200_FMT_INT4, B200_FMT_INT8
+from ._lib import B200_FMT_F16, B200_FMT_INT4, B200_FMT_INT8, B200_FMT_INT8G
 
 
 @dataclasses.dataclass
@@ -32,7 +32,7 @@ class ModelConfig:
     vocab: int
     rope_base: float = 500000.0
     eps: float = 1e-5
-    quant: str = "int4"          # "f16" | "int8" | "int4"
+    quant: str = "int4"          # "f16" | "int8" (per column) | "int4" (group 128) | "int8g" (8-bit group 128)
     tokens_per_block: int = 64   # KVCacheConfig.seq_size_per_block default (ConfigModules.h:174)
 
 
@@ -42,7 +42,7 @@ TINY = ModelConfig("tiny", 512, 2, 4, 2, 128, 512, 1024, tokens_per_block=16)
 
 
 def _fmt(q: str) -> int:
-    return {"f16": B200_FMT_F16, "int8": B200_FMT_INT8, "int4": B200_FMT_INT4}[q]
+    return {"f16": B200_FMT_F16, "int8": B200_FMT_INT8, "int4": B200_FMT_INT4, "int8g": B200_FMT_INT8G}[q]
 
 
 def weight_bytes(cfg: ModelConfig, K: int, N: int) -> float:
@@ -52,6 +52,8 @@ def weight_bytes(cfg: ModelConfig, K: int, N: int) -> float:
         return E / 2 + E / 128 * 4
     if cfg.quant == "int8":
         return E + 2 * N
+    if cfg.quant == "int8g":
+        return E + E / 128 * 4
     return 2 * E
 
 
@@ -99,6 +101,11 @@ class DecodeStep:
                     w, s, zs = (ops.interleave_gate_up(w, gi, packed_int4=True), ops.interleave_gate_up(s, gi),
                                 ops.interleave_gate_up(zs, gi))
                 return ops.pack_w4(w, s, zs)
+            if fmt == "int8g":
+                w, s, zs = w.to(device), s.to(device), zs.to(device)
+                if gi:
+                    w, s, zs = ops.interleave_gate_up(w, gi), ops.interleave_gate_up(s, gi), ops.interleave_gate_up(zs, gi)
+                return ops.pack_w8g(w, s, zs)
             if fmt == "int8":
                 w, s = w.to(device), s.to(device)
                 if gi:
@@ -118,6 +125,12 @@ class DecodeStep:
                 z = torch.randint(0, 16, (K // 128, N), generator=gg, device=device)
                 zs = ((8 - z).to(dtype) * s).to(dtype)
                 refw = ("int4", qp, s, zs)
+            elif quant == "int8g":
+                q8 = torch.randint(-128, 128, (K, N), generator=gg, device=device, dtype=torch.int8)
+                s = (torch.randn(K // 128, N, generator=gg, device=device).abs() * 6e-4 + 6e-5).to(dtype)
+                z = torch.randint(0, 256, (K // 128, N), generator=gg, device=device)
+                zs = ((128 - z).to(dtype) * s).to(dtype)
+                refw = ("int8g", q8, s, zs)
             elif quant == "int8":
                 q8 = torch.randint(-128, 128, (K, N), generator=gg, device=device, dtype=torch.int8)
                 s = (torch.randn(N, generator=gg, device=device).abs() * 2e-4 + 1e-5).to(dtype)

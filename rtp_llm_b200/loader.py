@@ -78,7 +78,7 @@ class B200Loader:
         self.r, self.q, self.device, self.act_dtype, self.align, self.fuse_silu = reader, quant, torch.device(device), act_dtype, align_size, fuse_silu
         self.impl = B200Impl(device, act_dtype)
 
-    # ---- group-wise INT4 (GPTQ / AWQ)
+    # ---- group-wise INT4 / INT8 (GPTQ / AWQ)
     def _triple(self, prefix: str):
         return self.r.get(prefix + QW), self.r.get(prefix + QZ), self.r.get(prefix + QS)
 
@@ -87,9 +87,9 @@ class B200Loader:
         nibbles, zeros_x_scales fp16 [K/g, N], scales fp16 [K/g, N]) -- what preprocess_groupwise_weight_params computes before
         its device-specific re-layout (device_impl.py:242-300)."""
         q = self.q
-        if q.bits != 4:
-            raise ValueError("8-bit group-wise (GPTQ/AWQ W8) checkpoints are outside the built scope")
-        pad_div = 32 // q.bits
+        if q.bits not in (4, 8):
+            raise ValueError(f"group-wise checkpoints: bits must be 4 or 8, got {q.bits}")
+        pad_div = 32 // q.bits                                        # group_wise_quant_weight.py:130
         qws, qzs, qss = zip(*[self._triple(p) for p in prefixes])
         if pad_out:                                                   # w1 / w3: the inter size is their OUTPUT axis
             qws = [pad_dim(w, pad_out if q.gptq else pad_out // pad_div, 1) for w in qws]
@@ -106,9 +106,10 @@ class B200Loader:
         q_packed, zs, scales = self.groupwise_tensors(prefixes, pad_in, pad_out)
         q_packed, zs, scales = q_packed.to(self.device), zs.to(self.act_dtype).to(self.device), scales.to(self.act_dtype).to(self.device)
         if gate_up_inter:
-            q_packed = ops.interleave_gate_up(q_packed, gate_up_inter, packed_int4=True)
+            q_packed = ops.interleave_gate_up(q_packed, gate_up_inter, packed_int4=self.q.bits == 4)
             zs, scales = ops.interleave_gate_up(zs, gate_up_inter), ops.interleave_gate_up(scales, gate_up_inter)
-        return ops.pack_w4(q_packed.contiguous(), scales.contiguous(), zs.contiguous(), self.q.group_size)
+        pack = ops.pack_w4 if self.q.bits == 4 else ops.pack_w8g     # 8-bit: q_s int8 [K, N], one byte per weight
+        return pack(q_packed.contiguous(), scales.contiguous(), zs.contiguous(), self.q.group_size)
 
     # ---- per-column INT8 (quantised at load time from FP16/BF16 weights) and plain FP16
     def _dense(self, prefixes, pad_in: int = 0, pad_out: int = 0, gate_up_inter: int = 0) -> ops.PackedWeight:

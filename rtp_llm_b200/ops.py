@@ -7,7 +7,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import B200_FMT_F16, B200_FMT_INT4, B200_FMT_INT8, B200Error, check
+from ._lib import B200_FMT_F16, B200_FMT_INT4, B200_FMT_INT8, B200_FMT_INT8G, B200Error, check
 
 
 def _stream() -> int:
@@ -187,6 +187,19 @@ def pack_w8(q: torch.Tensor, col_scale: torch.Tensor) -> PackedWeight:
     check(_lib.load().b200_pack_w8(_p(q), K, N, _p(blob), _stream()), "b200_pack_w8")
     PackedWeight._write_trailer(blob, B200_FMT_INT8, K, N, 0)
     return PackedWeight(B200_FMT_INT8, K, N, blob, col_scale)
+
+
+def pack_w8g(q: torch.Tensor, scales: torch.Tensor, zeros_x_scales: torch.Tensor, group: int = 128) -> PackedWeight:
+    """8-bit group-wise (GPTQ/AWQ W8): q int8 [K,N] (q_s = q_u - 128), scales / zeros_x_scales [K/g,N] in the activation dtype."""
+    _cuda_contig(q, scales, zeros_x_scales)
+    K, N = q.shape
+    n = _lib.load().b200_wo_gemm_packed_bytes(B200_FMT_INT8G, K, N)
+    if n == 0:
+        raise B200Error(f"pack_w8g: unsupported shape K={K} N={N}")
+    blob = torch.empty(int(n) + _TRAILER_BYTES, dtype=torch.uint8, device=q.device)
+    check(_lib.load().b200_pack_w8g(_p(q), _p(scales), _p(zeros_x_scales), K, N, group, _p(blob), _stream()), "b200_pack_w8g")
+    PackedWeight._write_trailer(blob, B200_FMT_INT8G, K, N, group)
+    return PackedWeight(B200_FMT_INT8G, K, N, blob)
 
 
 def pack_f16(w_kn: torch.Tensor) -> PackedWeight:

@@ -95,7 +95,8 @@ def make_comm(device: torch.device, group=None, kind: str = "peer"):
 # The reference's tensor-parallel split (rtp_llm/utils/model_weight.py:1489-1580): qkv column-parallel BY HEAD (sp_head,
 # :472-491), o row-parallel (sp_0), w1/w3 column-parallel (ffn_sp_neg1_w13, :997), w2 row-parallel (ffn_sp_0, :238),
 # scales / zeros split alongside, lm_head vocab rows (sp_0_pad8, :1491). Weights are the loader's UN-permuted tuples
-# (fmt, w, scales, zeros_x_scales): int4 w = uint8 [K, N/2]; int8 w = int8 [K, N], scales [N]; f16 w = [K, N].
+# (fmt, w, scales, zeros_x_scales): int4 w = uint8 [K, N/2]; int8 w = int8 [K, N], scales [N]; int8g w = int8 [K, N], scales /
+# zeros_x_scales [K/g, N]; f16 w = [K, N].
 
 def _cols(wt, col_ranges):
     """Select logical output columns [a, b) ranges of a reference-layout weight tuple."""
@@ -106,6 +107,9 @@ def _cols(wt, col_ranges):
         return (fmt, wq, torch.cat([s[:, a:b] for a, b in col_ranges], 1).contiguous(),
                 torch.cat([zs[:, a:b] for a, b in col_ranges], 1).contiguous())
     wq = torch.cat([w[:, a:b] for a, b in col_ranges], dim=1).contiguous()
+    if fmt == "int8g":
+        return (fmt, wq, torch.cat([s[:, a:b] for a, b in col_ranges], 1).contiguous(),
+                torch.cat([zs[:, a:b] for a, b in col_ranges], 1).contiguous())
     if fmt == "int8":
         return (fmt, wq, torch.cat([s[a:b] for a, b in col_ranges]).contiguous(), None)
     return (fmt, wq, None, None)
@@ -114,8 +118,8 @@ def _cols(wt, col_ranges):
 def _rows(wt, a, b, group=128):
     """Select input rows (the contraction dim) [a, b); group-wise scales follow in units of `group`."""
     fmt, w, s, zs = wt
-    if fmt == "int4":
-        assert a % group == 0 and b % group == 0, "row-parallel INT4 shards must align to the quantisation group"
+    if fmt in ("int4", "int8g"):
+        assert a % group == 0 and b % group == 0, "row-parallel group-wise shards must align to the quantisation group"
         return (fmt, w[a:b].contiguous(), s[a // group:b // group].contiguous(), zs[a // group:b // group].contiguous())
     return (fmt, w[a:b].contiguous(), s, None)
 

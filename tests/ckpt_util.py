@@ -12,39 +12,44 @@ import torch
 AWQ_ORDER = [0, 2, 4, 6, 1, 3, 5, 7]
 
 
-def _pack_cols(vals, order):
-    """vals [R, C] in 0..15 -> int32 [R, C/8], nibble j of a word = column order[j] of its group of 8."""
+def _pack_cols(vals, order, bits=4):
+    """vals [R, C] in 0..2^bits-1 -> int32 [R, C*bits/32]: field j of a run of 8 columns = column order[j] of the run (4-bit: one
+    word per run; 8-bit: two words, the reference applies reverse_awq_order over runs of 8 either way, device_impl.py:163-171)."""
     R, C = vals.shape
-    v = vals.reshape(R, C // 8, 8).astype(np.uint32)
-    out = np.zeros((R, C // 8), np.uint32)
+    v = vals.reshape(R, C // 8, 8).astype(np.uint64)
+    out = np.zeros((R, C // 8), np.uint64)
     for j, src in enumerate(order):
-        out |= v[:, :, src] << (4 * j)
-    return out.view(np.int32)
+        out |= v[:, :, src] << np.uint64(bits * j)
+    if bits == 4:
+        return out.astype(np.uint32).view(np.int32)
+    return np.ascontiguousarray(out).view(np.uint32).reshape(R, C // 4).view(np.int32)     # little endian: low word first
 
 
-def _pack_rows(vals):
-    """vals [R, C] -> int32 [R/8, C], nibble j of a word = row 8*i + j."""
+def _pack_rows(vals, bits=4):
+    """vals [R, C] -> int32 [R*bits/32, C], field j of a word = row per*i + j."""
+    per = 32 // bits
     R, C = vals.shape
-    v = vals.reshape(R // 8, 8, C).astype(np.uint32)
-    out = np.zeros((R // 8, C), np.uint32)
-    for j in range(8):
-        out |= v[:, j, :] << (4 * j)
+    v = vals.reshape(R // per, per, C).astype(np.uint32)
+    out = np.zeros((R // per, C), np.uint32)
+    for j in range(per):
+        out |= v[:, j, :] << (bits * j)
     return out.view(np.int32)
 
 
-def make_layer(rng, method, K, N, group=128):
-    q = rng.integers(0, 16, (K, N))
-    z = rng.integers(1 if method == "gptq" else 0, 16, (K // group, N))
-    s = (np.abs(rng.standard_normal((K // group, N))) * 0.01 + 1e-3).astype(np.float16)
+def make_layer(rng, method, K, N, group=128, bits=4):
+    top = 1 << bits
+    q = rng.integers(0, top, (K, N))
+    z = rng.integers(1 if method == "gptq" else 0, top, (K // group, N))
+    s = (np.abs(rng.standard_normal((K // group, N))) * (0.01 if bits == 4 else 6e-4) + (1e-3 if bits == 4 else 6e-5)).astype(np.float16)
     dense = ((q - np.repeat(z, group, 0)).astype(np.float32) * np.repeat(s.astype(np.float32), group, 0))
     if method == "gptq":
-        t = dict(qweight=_pack_rows(q), qzeros=_pack_cols(z - 1, list(range(8))), scales=s)
+        t = dict(qweight=_pack_rows(q, bits), qzeros=_pack_cols(z - 1, list(range(8)), bits), scales=s)
     else:
-        t = dict(qweight=_pack_cols(q, AWQ_ORDER), qzeros=_pack_cols(z, AWQ_ORDER), scales=s)
+        t = dict(qweight=_pack_cols(q, AWQ_ORDER, bits), qzeros=_pack_cols(z, AWQ_ORDER, bits), scales=s)
     return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in t.items()}, dense
 
 
-def write_checkpoint(path, rng, method, hidden, heads, kv_heads, head_dim, inter, group=128):
+def write_checkpoint(path, rng, method, hidden, heads, kv_heads, head_dim, inter, group=128, bits=4):
     """One decoder layer in HF naming; returns the dense [K, N] weights by logical name."""
     from safetensors.torch import save_file
     shapes = dict(q=(hidden, heads * head_dim), k=(hidden, kv_heads * head_dim), v=(hidden, kv_heads * head_dim),
@@ -55,7 +60,7 @@ def write_checkpoint(path, rng, method, hidden, heads, kv_heads, head_dim, inter
     for key, (K, N) in shapes.items():
         names[key] = f"model.layers.0.{hf[key]}"
         if method in ("gptq", "awq"):
-            t, d = make_layer(rng, method, K, N, group)
+            t, d = make_layer(rng, method, K, N, group, bits)
             for suffix, val in t.items():
                 tensors[f"{names[key]}.{suffix}"] = val
         else:

@@ -43,7 +43,7 @@ __global__ void ref_paged_decode_attn_kernel(const T* __restrict__ q, T* __restr
 }
 
 // Y = X . W' from the UN-permuted reference tensors (fmt 0: W[K][N] T; 1: q int8 [K][N] + scale[N]; 2: q_packed [K][N/2]
-// + scales/zs [K/g][N]); one thread per output, fp32 accumulate, W' rounded to T exactly like the oracle.
+// + scales/zs [K/g][N]; 3: q_s int8 [K][N] + scales/zs [K/g][N]); one thread per output, fp32 accumulate, W' rounded to T exactly like the oracle.
 template <typename T>
 __global__ void ref_dequant_gemm_kernel(const T* __restrict__ x, int B, int K, int N, int fmt,
                                         const void* __restrict__ w, const T* __restrict__ scales,
@@ -58,6 +58,9 @@ __global__ void ref_dequant_gemm_kernel(const T* __restrict__ x, int B, int K, i
             wv = to_f32<T>(reinterpret_cast<const T*>(w)[(size_t)k * N + n]);
         } else if (fmt == 1) {
             wv = to_f32<T>(from_f32<T>((float)reinterpret_cast<const int8_t*>(w)[(size_t)k * N + n] * to_f32<T>(scales[n])));
+        } else if (fmt == 3) {   // 8-bit group-wise
+            wv = to_f32<T>(from_f32<T>(fmaf((float)reinterpret_cast<const int8_t*>(w)[(size_t)k * N + n],
+                                           to_f32<T>(scales[(size_t)(k / group) * N + n]), to_f32<T>(zs[(size_t)(k / group) * N + n]))));
         } else {
             const uint8_t byte = reinterpret_cast<const uint8_t*>(w)[(size_t)k * (N / 2) + n / 2];
             int nib = (n & 1) ? (byte >> 4) : (byte & 0xF);

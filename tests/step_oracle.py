@@ -17,6 +17,8 @@ def _gemm(x_bits, ref, is_bf16=False):
     fmt, w, s, zs = ref
     if fmt == "int4":
         return orc.dequant_gemm(x_bits, "int4", w.numpy(), scales=_bits(s), zeros_x_scales=_bits(zs), group=128, is_bf16=is_bf16)
+    if fmt == "int8g":
+        return orc.dequant_gemm(x_bits, "int8g", w.numpy(), scales=_bits(s), zeros_x_scales=_bits(zs), group=128, is_bf16=is_bf16)
     if fmt == "int8":
         return orc.dequant_gemm(x_bits, "int8", w.numpy(), scales=_bits(s), is_bf16=is_bf16)
     return orc.dequant_gemm(x_bits, "f16", _bits(w), is_bf16=is_bf16)

@@ -6,7 +6,7 @@ pytestmark = pytest.mark.gpu
 from tests.step_oracle import check_tiny_step  # noqa: E402
 
 
-@pytest.mark.parametrize("quant", ["int4", "int8", "f16"])
+@pytest.mark.parametrize("quant", ["int4", "int8", "int8g", "f16"])
 def test_tiny_decode_step_matches_oracle(quant):
     check_tiny_step(torch.device("cuda:0"), quant=quant, batch=3, ctx=40)
 

@@ -14,13 +14,15 @@ from tests import ckpt_util  # noqa: E402
 dev = torch.device("cuda")
 
 
-@pytest.mark.parametrize("method", ["gptq", "awq", "int8", "none"])
+@pytest.mark.parametrize("method", ["gptq", "awq", "int8", "none", "gptq8", "awq8"])
 def test_layer_through_the_loader(tmp_path, method):
     rng = np.random.default_rng(7)
     path = str(tmp_path / "layer.safetensors")
     hidden, heads, kvh, D, inter, align = 512, 4, 2, 128, 640, 256
-    names, dense = ckpt_util.write_checkpoint(path, rng, method, hidden, heads, kvh, D, inter)
-    ld = B200Loader(CheckpointReader(path), QuantConfig(method), device=dev, align_size=align)
+    bits = 8 if method.endswith("8") and method != "int8" else 4
+    method = method[:-1] if bits == 8 else method
+    names, dense = ckpt_util.write_checkpoint(path, rng, method, hidden, heads, kvh, D, inter, bits=bits)
+    ld = B200Loader(CheckpointReader(path), QuantConfig(method, bits=bits), device=dev, align_size=align)
     L = ld.layer(names, inter=inter)
     inter_p = 768
     x = torch.from_numpy(rng.standard_normal((9, hidden)).astype(np.float32)).half().to(dev)

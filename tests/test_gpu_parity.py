@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 from oracle import oracle as orc  # noqa: E402
 from rtp_llm_b200 import ops  # noqa: E402
-from rtp_llm_b200._lib import B200_FMT_F16, B200_FMT_INT4, B200_FMT_INT8  # noqa: E402
+from rtp_llm_b200._lib import B200_FMT_F16, B200_FMT_INT4, B200_FMT_INT8, B200_FMT_INT8G  # noqa: E402
 from tools import gpu_probe as probe  # noqa: E402
 
 
@@ -203,7 +203,7 @@ GEMM_SMALL = [
 ]
 
 
-@pytest.mark.parametrize("fmt", [B200_FMT_F16, B200_FMT_INT8, B200_FMT_INT4], ids=["f16", "int8", "int4"])
+@pytest.mark.parametrize("fmt", [B200_FMT_F16, B200_FMT_INT8, B200_FMT_INT4, B200_FMT_INT8G], ids=["f16", "int8", "int4", "int8g"])
 @pytest.mark.parametrize("case", GEMM_SMALL, ids=[c[0] for c in GEMM_SMALL])
 def test_gemm_vs_oracle(fmt, case):
     """Tolerance (stated because the reference has no weight-only GEMM kernel to pin against):
@@ -216,6 +216,7 @@ def test_gemm_vs_oracle(fmt, case):
                                  ("int4 Llama w2 B32", B200_FMT_INT4, 32, 14336, 4096),
                                  ("int4 Llama w13 B64", B200_FMT_INT4, 64, 4096, 28672),
                                  ("int8 Llama o B32", B200_FMT_INT8, 32, 4096, 4096),
+                                 ("int8 group-wise Llama qkv B32", B200_FMT_INT8G, 32, 4096, 6144),
                                  ("f16 lm_head slice B32", B200_FMT_F16, 32, 4096, 16032)], ids=lambda c: c[0])
 def test_gemm_full_size_vs_oracle(cfg):
     """BASELINE shapes: checked against the CPU oracle (and, as a second opinion, the naive GPU kernel)."""
@@ -246,7 +247,7 @@ def test_gemm_persistent_kernel_standalone(case):
     _run(probe.gemm_silu_case, name + " silu", fmt, 7, 512, 192, env=env)
 
 
-@pytest.mark.parametrize("fmt", [B200_FMT_F16, B200_FMT_INT8, B200_FMT_INT4], ids=["f16", "int8", "int4"])
+@pytest.mark.parametrize("fmt", [B200_FMT_F16, B200_FMT_INT8, B200_FMT_INT4, B200_FMT_INT8G], ids=["f16", "int8", "int4", "int8g"])
 def test_gemm_fused_silu_mul_vs_oracle(fmt):
     _run(probe.gemm_silu_case, "silu direct", fmt, 7, 256, 192)
     _run(probe.gemm_silu_case, "silu cluster split", fmt, 32, 1024, 128, env={"B200_GEMM_SPLITK": 4})

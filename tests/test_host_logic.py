@@ -22,6 +22,17 @@ def test_unpack_groupwise_torch_matches_reference(golden_dir, fmt):
     assert np.array_equal(sc.numpy().view(np.uint16), g["scales_out"].view(np.uint16))
 
 
+@pytest.mark.parametrize("fmt", ["gptq", "awq"])
+def test_unpack_groupwise_8bit_torch_matches_reference(golden_dir, fmt):
+    g = np.load(os.path.join(golden_dir, f"quant_unpack8_{fmt}.npz"))
+    impl = device.B200Impl(device="cpu")
+    q, zs, sc = impl.unpack_groupwise(torch.from_numpy(g["qweight"]), torch.from_numpy(g["qzeros"]),
+                                      torch.from_numpy(g["scales"]), gptq=fmt == "gptq", awq=fmt == "awq", weight_bits=8)
+    assert q.dtype == torch.int8 and np.array_equal(q.numpy(), g["q"])
+    assert np.array_equal(zs.numpy().view(np.uint16), g["zeros_x_scales"].view(np.uint16))
+    assert np.array_equal(sc.numpy().view(np.uint16), g["scales_out"].view(np.uint16))
+
+
 def test_int8_quantiser_matches_reference(golden_dir):
     g = np.load(os.path.join(golden_dir, "quant_int8.npz"))
     q, s = device.B200Impl(device="cpu").symmetric_quantize_last_axis_of_batched_matrix(torch.from_numpy(g["weight"]))

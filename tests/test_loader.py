@@ -11,6 +11,9 @@ from tests import ckpt_util
 
 
 def _dense_from_unpacked(q_packed, zs, scales, group=128):
+    if q_packed.dtype == torch.int8:                                         # 8-bit group-wise: q_s, one byte per weight
+        return (q_packed.numpy().astype(np.float32) * np.repeat(scales.float().numpy(), group, 0)
+                + np.repeat(zs.float().numpy(), group, 0))
     b = q_packed.numpy().astype(np.uint8)
     lo, hi = (b & 0xF).astype(np.int16), (b >> 4).astype(np.int16)
     q = np.empty((b.shape[0], b.shape[1] * 2), np.int16)
@@ -19,13 +22,14 @@ def _dense_from_unpacked(q_packed, zs, scales, group=128):
     return q * np.repeat(scales.float().numpy(), group, 0) + np.repeat(zs.float().numpy(), group, 0)
 
 
+@pytest.mark.parametrize("bits", [4, 8])
 @pytest.mark.parametrize("method", ["gptq", "awq"])
-def test_groupwise_checkpoint_unpacks_to_its_dense_meaning(tmp_path, method):
+def test_groupwise_checkpoint_unpacks_to_its_dense_meaning(tmp_path, method, bits):
     rng = np.random.default_rng(5)
     path = str(tmp_path / "layer.safetensors")
     hidden, heads, kvh, D, inter = 256, 4, 2, 64, 384
-    names, dense = ckpt_util.write_checkpoint(path, rng, method, hidden, heads, kvh, D, inter)
-    ld = B200Loader(CheckpointReader(path), QuantConfig(method), device="cpu")
+    names, dense = ckpt_util.write_checkpoint(path, rng, method, hidden, heads, kvh, D, inter, bits=bits)
+    ld = B200Loader(CheckpointReader(path), QuantConfig(method, bits=bits), device="cpu")
     # qkv: q | k | v merged along the output axis
     got = _dense_from_unpacked(*ld.groupwise_tensors([names["q"], names["k"], names["v"]]))
     np.testing.assert_allclose(got, np.concatenate([dense["q"], dense["k"], dense["v"]], 1), atol=2e-3, rtol=2e-3)
@@ -47,9 +51,9 @@ def test_pad_dim_matches_reference_pad_semantics():
     assert pad_dim(t, 4, 0).shape == (4, 3) and int(pad_dim(t, 4, 0)[2:].abs().sum()) == 0
 
 
-def test_eight_bit_groupwise_is_rejected_loudly(tmp_path):
+def test_unsupported_bit_widths_are_rejected_loudly(tmp_path):
     rng = np.random.default_rng(1)
     path = str(tmp_path / "l.safetensors")
     names, _ = ckpt_util.write_checkpoint(path, rng, "gptq", 128, 2, 1, 64, 128)
     with pytest.raises(ValueError):
-        B200Loader(CheckpointReader(path), QuantConfig("gptq", bits=8), device="cpu").groupwise_tensors([names["o"]])
+        B200Loader(CheckpointReader(path), QuantConfig("gptq", bits=3), device="cpu").groupwise_tensors([names["o"]])

@@ -21,6 +21,32 @@ def test_unpack_groupwise_matches_reference_loader(golden_dir, fmt):
     assert np.array_equal(sc.view(np.uint16), g["scales_out"].view(np.uint16))
 
 
+@pytest.mark.parametrize("fmt", ["gptq", "awq"])
+def test_unpack_groupwise_8bit_matches_reference_loader(golden_dir, fmt):
+    """weight_bits == 8 branch of preprocess_groupwise_weight_params (device_impl.py:256-258), goldens by the reference's code."""
+    g = _load(golden_dir, f"quant_unpack8_{fmt}.npz")
+    q, zs, sc = orc.unpack_groupwise_int8(g["qweight"], g["qzeros"], g["scales"], int(g["group"]), fmt == "gptq")
+    assert q.dtype == np.int8 and np.array_equal(q, g["q"])
+    assert np.array_equal(zs.view(np.uint16), g["zeros_x_scales"].view(np.uint16))
+    assert np.array_equal(sc.view(np.uint16), g["scales_out"].view(np.uint16))
+
+
+def test_int8_groupwise_gemm_oracle_consistency():
+    """fmt int8g of the C oracle against the numpy dequant formula W' = q_s * s + zeros_x_scales (one rounding) + fp64 matmul."""
+    rng = np.random.default_rng(5)
+    B, K, N = 3, 256, 96
+    x = (rng.standard_normal((B, K)) * 0.5).astype(np.float16)
+    q = rng.integers(-128, 128, (K, N), dtype=np.int8)
+    s = (np.abs(rng.standard_normal((K // 128, N))) * 6e-4 + 6e-5).astype(np.float16)
+    zs = ((128 - rng.integers(0, 256, (K // 128, N))).astype(np.float32) * s.astype(np.float32)).astype(np.float16)
+    for fast in (False, True):
+        y = orc.from_bits(orc.dequant_gemm(x.view(np.uint16), "int8g", q, scales=s, zeros_x_scales=zs, group=128, fast=fast), False)
+        w = orc.dequant_np("int8g", q, s, zs, 128) if not fast else (q.astype(np.float32) * np.repeat(s.astype(np.float32), 128, 0)
+                                                                        + np.repeat(zs.astype(np.float32), 128, 0))
+        exp = x.astype(np.float64) @ w.astype(np.float64)
+        assert np.allclose(y, exp, rtol=2e-3, atol=2e-3), fast
+
+
 def test_int8_per_column_quantiser_matches_reference(golden_dir):
     g = _load(golden_dir, "quant_int8.npz")
     q, s = orc.quantize_int8_per_col(g["weight"])

@@ -25,6 +25,10 @@ def _weights(fmt):
             s = (torch.randn(K // 128, N, generator=g).abs() * 0.01 + 1e-3).half()
             z = torch.randint(0, 16, (K // 128, N), generator=g)
             return ("int4", qp, s, ((8 - z).half() * s).half())
+        if fmt == "int8g":
+            s = (torch.randn(K // 128, N, generator=g).abs() * 6e-4 + 6e-5).half()
+            z = torch.randint(0, 256, (K // 128, N), generator=g)
+            return ("int8g", torch.randint(-128, 128, (K, N), generator=g, dtype=torch.int8), s, ((128 - z).half() * s).half())
         if fmt == "int8":
             return ("int8", torch.randint(-128, 128, (K, N), generator=g, dtype=torch.int8),
                     (torch.randn(N, generator=g).abs() * 2e-3 + 1e-4).half(), None)
@@ -40,6 +44,8 @@ def _gemm(x_bits, wt):
     fmt, w, s, zs = wt
     if fmt == "int4":
         return orc.dequant_gemm(x_bits, "int4", w.numpy(), scales=_bits(s), zeros_x_scales=_bits(zs), group=128)
+    if fmt == "int8g":
+        return orc.dequant_gemm(x_bits, "int8g", w.numpy(), scales=_bits(s), zeros_x_scales=_bits(zs), group=128)
     if fmt == "int8":
         return orc.dequant_gemm(x_bits, "int8", w.numpy(), scales=_bits(s))
     return orc.dequant_gemm(x_bits, "f16", _bits(w))
@@ -78,7 +84,7 @@ def _worker(rank, world, port, fmt, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("fmt", ["int4", "int8", "f16"])
+@pytest.mark.parametrize("fmt", ["int4", "int8", "int8g", "f16"])
 def test_tp2_sharded_layer_equals_unsharded(fmt):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import oracle as orc  # noqa: E402
 from rtp_llm_b200 import ops  # noqa: E402
-from rtp_llm_b200._lib import B200_FMT_F16, B200_FMT_INT4, B200_FMT_INT8  # noqa: E402
+from rtp_llm_b200._lib import B200_FMT_F16, B200_FMT_INT4, B200_FMT_INT8, B200_FMT_INT8G  # noqa: E402
 from tests import ref_kernels as refk  # noqa: E402  (naive CUDA-core second opinion, test-only library)
 
 dev = torch.device("cuda:0")
@@ -140,6 +140,19 @@ def make_w4(K, N, seed=1, simple=False):
     return qp, s, zs
 
 
+def make_w8g(K, N, seed=1, simple=False):
+    rng = np.random.default_rng(seed)
+    q = rng.integers(-128, 128, (K, N)).astype(np.int8)
+    G = K // 128
+    if simple:
+        s, zs = np.ones((G, N), np.float16), np.zeros((G, N), np.float16)
+    else:   # realistic magnitude: W' ~ 0.02 like an 8-bit GPTQ layer (range / 255 per group)
+        s = (np.abs(rng.standard_normal((G, N))) * 2e-4 + 3e-4).astype(np.float16)
+        z = rng.integers(0, 256, (G, N))
+        zs = ((128 - z).astype(np.float32) * s.astype(np.float32)).astype(np.float16)
+    return q, s, zs
+
+
 def gemm_case(name, fmt, B, K, N, dtype=torch.float16, simple=False, onehot=False, env=None, bias=False, big=False):
     def fn():
         old = {}
@@ -161,6 +174,12 @@ def gemm_case(name, fmt, B, K, N, dtype=torch.float16, simple=False, onehot=Fals
                 qd = torch.from_numpy(qp).to(dev)
                 sd, zd = torch.from_numpy(s).to(dtype).to(dev), torch.from_numpy(zs).to(dtype).to(dev)
                 w = ops.pack_w4(qd, sd, zd)
+                ref = refk.ref_dequant_gemm(x, fmt, qd, sd, zd, 128, bias_t)
+            elif fmt == B200_FMT_INT8G:
+                q8, s, zs = make_w8g(K, N, simple=simple)
+                qd = torch.from_numpy(q8).to(dev)
+                sd, zd = torch.from_numpy(s).to(dtype).to(dev), torch.from_numpy(zs).to(dtype).to(dev)
+                w = ops.pack_w8g(qd, sd, zd)
                 ref = refk.ref_dequant_gemm(x, fmt, qd, sd, zd, 128, bias_t)
             elif fmt == B200_FMT_INT8:
                 q8 = rng.integers(-128, 128, (K, N)).astype(np.int8)
@@ -189,6 +208,9 @@ def gemm_case(name, fmt, B, K, N, dtype=torch.float16, simple=False, onehot=Fals
                 is_bf16 = dtype == torch.bfloat16
                 if fmt == B200_FMT_INT4:
                     exp = orc.dequant_gemm(bits(x), "int4", qp, scales=bits(sd), zeros_x_scales=bits(zd), group=128,
+                                           bias=bits(bias_t) if bias else None, is_bf16=is_bf16)
+                elif fmt == B200_FMT_INT8G:
+                    exp = orc.dequant_gemm(bits(x), "int8g", q8, scales=bits(sd), zeros_x_scales=bits(zd), group=128,
                                            bias=bits(bias_t) if bias else None, is_bf16=is_bf16)
                 elif fmt == B200_FMT_INT8:
                     exp = orc.dequant_gemm(bits(x), "int8", q8, scales=bits(sd), bias=bits(bias_t) if bias else None,
@@ -226,6 +248,11 @@ def gemm_silu_case(name, fmt, B, K, inter, dtype=torch.float16, env=None):
                 w = ops.pack_w4(ops.interleave_gate_up(qd, inter, packed_int4=True), ops.interleave_gate_up(sd, inter),
                                 ops.interleave_gate_up(zd, inter))
                 gu = orc.dequant_gemm(bits(x), "int4", qp, scales=bits(sd), zeros_x_scales=bits(zd), group=128)
+            elif fmt == B200_FMT_INT8G:
+                q8, s, zs = make_w8g(K, N)
+                qd, sd, zd = torch.from_numpy(q8).to(dev), torch.from_numpy(s).to(dtype).to(dev), torch.from_numpy(zs).to(dtype).to(dev)
+                w = ops.pack_w8g(ops.interleave_gate_up(qd, inter), ops.interleave_gate_up(sd, inter), ops.interleave_gate_up(zd, inter))
+                gu = orc.dequant_gemm(bits(x), "int8g", q8, scales=bits(sd), zeros_x_scales=bits(zd), group=128)
             elif fmt == B200_FMT_INT8:
                 q8 = rng.integers(-128, 128, (K, N)).astype(np.int8)
                 s = (np.abs(rng.standard_normal(N)) * 2e-4 + 3e-4).astype(np.float32)
