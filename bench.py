@@ -323,7 +323,8 @@ def main():
             "config": {"workload": workload, "global_batch": args.batch, "seq_len": args.ctx,
                        "parallelism": f"tp{tp}", "tp_allreduce": (args.comm if tp > 1 else None), "page_size": cfg.tokens_per_block, "cuda_graph": True,
                        "l2": "inputs larger than L2 (each step streams %.2f GB of weights + KV per GPU)" % (ab["total"] / 1e9),
-                       "pdl": bool(args.pdl), "decode_program": use_program},
+                       "pdl": bool(args.pdl), "decode_program": use_program,
+                       "gemm_reduce_scatter_fused": bool(getattr(model, "fuse_gemm_rs", False))},
             "e2e": {"value": args.batch / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": model.h2d_bytes(),
                     "d2h_bytes_per_step": model.d2h_bytes(), "ms_per_step": ms_e2e},
             "parity_check": parity_check,

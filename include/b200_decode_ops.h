@@ -235,6 +235,22 @@ int b200_peer_allreduce(const void* in, void* out, size_t bytes, int is_bf16, vo
 int b200_peer_allreduce_norm(const void* in, void* residual, const void* gamma, void* y, int is_bf16, int rows, int hidden,
                              float eps, void* const* regions, size_t max_message_bytes, int rank, int world, void* stream);
 
+/* GEMM + reduce-scatter in ONE kernel, for the row-parallel GEMMs (o, w2) under tensor parallelism (reference sequence:
+ * LinearBase.forward, then all_reduce(t, Group.TP): hybrid/causal_attention.py:90-92, dense_mlp.py:103-105). Same arguments
+ * and arithmetic as b200_wo_gemm; the epilogue pushes every output element another rank owns (rank r owns the r-th 1/world
+ * of the columns of every row) straight into that rank's reduce-scatter slot over NVLink while the tile is still in
+ * registers; the columns this rank owns are stored to y. MUST be followed on the same stream by b200_peer_gather_norm over
+ * the same y / regions with no other collective of this communicator in between (both derive the exchange epoch from the
+ * communicator's device-side call counter). Bits are those of b200_wo_gemm + b200_peer_allreduce_norm.
+ * N % 128 == 0, N % (8*world) == 0, N <= 8192, B*N*2 <= max_message_bytes, no SILU_MUL. */
+int b200_wo_gemm_rs(int fmt, int is_bf16, const void* x, int B, int K, int N, const void* w, const void* col_scale,
+                    const void* bias, void* y, void* workspace, size_t workspace_bytes, int flags, void* const* regions,
+                    size_t max_message_bytes, int rank, int world, void* stream);
+/* Second half of the fused exchange: reduce the own slice in rank order, all-gather, residual add, RMSNorm (the kernel of
+ * b200_peer_allreduce_norm without its scatter phase, which the GEMM epilogue already did). */
+int b200_peer_gather_norm(const void* in, void* residual, const void* gamma, void* y, int is_bf16, int rows, int hidden,
+                          float eps, void* const* regions, size_t max_message_bytes, int rank, int world, void* stream);
+
 /* Vocab-parallel greedy sampling: out[r] = argmax over the CONCATENATED vocabulary (rank r holds columns
  * [r*vocab_local, (r+1)*vocab_local), columns >= vocab_total are padding), lowest index on ties, identical on every rank.
  * Replaces the logits all-gather + argmax of cpp/models/PyWrappedModel.cc:915-936,1001-1052 for top_k == 1. */

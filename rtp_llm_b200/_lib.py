@@ -34,6 +34,8 @@ SIGNATURES = {
     "b200_wo_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "b200_wo_gemm": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_size_t, c_int, c_void_p]),
+    "b200_wo_gemm_rs": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_size_t, c_int, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "b200_add_rmsnorm": (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_float, c_void_p]),
     "b200_qk_rmsnorm": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_float, c_void_p]),
     "b200_silu_and_mul": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -47,6 +49,7 @@ SIGNATURES = {
     "b200_peer_open": (c_int, [c_void_p, c_void_p]),
     "b200_peer_allreduce": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
     "b200_peer_allreduce_norm": (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "b200_peer_gather_norm": (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "b200_peer_argmax": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "b200_program_create": (c_int, [c_void_p]),
     "b200_program_begin": (c_int, [c_void_p]),

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb200_decode.so")
 # translation units compile in parallel (the persistent-kernel instantiations dominate the build time)
-SOURCES = ["c_api.cu", "gemm_cluster.cu", "segment_f16.cu", "segment_bf16.cu"]
+SOURCES = ["c_api.cu", "gemm_cluster.cu", "gemm_cluster_rs.cu", "segment_f16.cu", "segment_bf16.cu"]
 NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
               "-Xcompiler", "-fPIC", "-DB200_BUILD"]
 if os.environ.get("B200_DEV"):           # developer build: clock64 timeline + ablation switches in the cluster GEMM (tools/gemm_trace.py)

@@ -651,8 +651,44 @@ size_t b200_wo_gemm_workspace_bytes(int max_batch, int N, int K) {
     return kGemmSemBytes + (part > sk ? part : sk);
 }
 
+namespace {
+struct RsDesc {
+    void* regions[kArMaxWorld];
+    size_t max_message_bytes;
+    int rank, world;
+};
+int wo_gemm_impl(int fmt, int is_bf16, const void* x, int B, int K, int N, const void* w, const void* col_scale,
+                 const void* bias, void* y, void* workspace, size_t workspace_bytes, int flags, const RsDesc* rs, void* stream);
+int fill_ar_params(PeerArParams& p, void* const* regions, size_t max_message_bytes, int rank, int world);
+}  // namespace
+
 int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const void* w, const void* col_scale,
                  const void* bias, void* y, void* workspace, size_t workspace_bytes, int flags, void* stream) {
+    return wo_gemm_impl(fmt, is_bf16, x, B, K, N, w, col_scale, bias, y, workspace, workspace_bytes, flags, nullptr, stream);
+}
+
+int b200_wo_gemm_rs(int fmt, int is_bf16, const void* x, int B, int K, int N, const void* w, const void* col_scale,
+                    const void* bias, void* y, void* workspace, size_t workspace_bytes, int flags, void* const* regions,
+                    size_t max_message_bytes, int rank, int world, void* stream) {
+    ARG_CHECK(regions, "wo_gemm_rs: null regions");
+    ARG_CHECK(world >= 2 && world <= kArMaxWorld && rank >= 0 && rank < world, "wo_gemm_rs: bad rank/world %d/%d", rank, world);
+    ARG_CHECK(N % 128 == 0 && N % (8 * world) == 0 && N <= 8192, "wo_gemm_rs: N=%d must be a multiple of 128 and of 8*world, <= 8192", N);
+    ARG_CHECK((size_t)B * N * 2 <= max_message_bytes, "wo_gemm_rs: message of %zu bytes exceeds the region", (size_t)B * N * 2);
+    ARG_CHECK(!(flags & B200_GEMM_SILU_MUL), "wo_gemm_rs: SILU_MUL cannot be combined with the reduce-scatter push");
+    RsDesc d{};
+    for (int r = 0; r < world; ++r) {
+        ARG_CHECK(regions[r], "wo_gemm_rs: region %d is null", r);
+        d.regions[r] = regions[r];
+    }
+    d.max_message_bytes = max_message_bytes;
+    d.rank = rank;
+    d.world = world;
+    return wo_gemm_impl(fmt, is_bf16, x, B, K, N, w, col_scale, bias, y, workspace, workspace_bytes, flags, &d, stream);
+}
+
+namespace {
+int wo_gemm_impl(int fmt, int is_bf16, const void* x, int B, int K, int N, const void* w, const void* col_scale,
+                 const void* bias, void* y, void* workspace, size_t workspace_bytes, int flags, const RsDesc* rs, void* stream) {
     if (B == 0) return B200_OK;
     ARG_CHECK(fmt == B200_FMT_F16 || fmt == B200_FMT_INT8 || fmt == B200_FMT_INT4 || fmt == B200_FMT_INT8G,
               "wo_gemm: unknown weight format %d", fmt);
@@ -683,7 +719,7 @@ int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const
     // measured on B200 at B=32 (profiles/r02_gemm_paths.txt) the cluster kernel is faster for every Llama-3-8B shape;
     // B200_GEMM_PERSISTENT=1 routes stand-alone calls through the persistent kernel too (experiments / tests).
     const bool seg_capable = (fmt == B200_FMT_INT8 || fmt == B200_FMT_INT4) && bpad <= 64;   // INT8G / FP16: cluster kernel only
-    const bool streamk = seg_capable && (recording_fused(kOpGemm) || env_int("B200_GEMM_PERSISTENT", 0));
+    const bool streamk = seg_capable && !rs && (recording_fused(kOpGemm) || env_int("B200_GEMM_PERSISTENT", 0));
     if (streamk) {
         ARG_CHECK(workspace && workspace_bytes >= kGemmSemBytes, "wo_gemm: workspace of at least %zu bytes required", kGemmSemBytes);
         int grid = 0;
@@ -720,10 +756,17 @@ int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const
         return launch_segment(is_bf16 != 0, bpad, fmt, &op, nullptr, 1, gbar, plan.used < grid ? plan.used : grid, use_pdl,
                               nullptr, (cudaStream_t)stream);
     }
-    if (g_rec)
+    if (g_rec) {
+        if (rs) {
+            const RsDesc d = *rs;
+            return rec_call([=](void* st) {
+                return wo_gemm_impl(fmt, is_bf16, x, B, K, N, w, col_scale, bias, y, workspace, workspace_bytes, flags, &d, st);
+            });
+        }
         return rec_call([=](void* st) {
             return b200_wo_gemm(fmt, is_bf16, x, B, K, N, w, col_scale, bias, y, workspace, workspace_bytes, flags, st);
         });
+    }
 
     // ---- FP16 weights / batches above 64: one kernel per GEMM, cluster split-K (gemm_cluster.cu)
     GemmParams p{};
@@ -745,7 +788,8 @@ int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const
     }
     p.dbg = env_int("B200_GEMM_DBG", 0);
 #endif
-    p.cluster_reduce = env_int("B200_GEMM_CLUSTER", 1) ? 1 : 0;   // split-K merge through DSMEM (cluster <= 8) vs global semaphores
+    p.cluster_reduce = (rs || env_int("B200_GEMM_CLUSTER", 1)) ? 1 : 0;   // split-K merge through DSMEM (cluster <= 8) vs global semaphores
+
     gemm_split(n_tiles, p.k_blocks, p.cluster_reduce ? 8 : 16, &p.nsplit, &p.kb_per_split);
     if (p.silu_mul && !p.cluster_reduce) {
         p.nsplit = 1;   // the fused activation is implemented for the direct and the cluster-merge epilogues
@@ -776,8 +820,23 @@ int b200_wo_gemm(int fmt, int is_bf16, const void* x, int B, int K, int N, const
     } else {
         wmap = xmap;  // unused by the kernel
     }
+    if (rs) {
+        GemmParamsRs prs{};
+        static_cast<GemmParams&>(prs) = p;
+        PeerArParams ap{};
+        int rc = fill_ar_params(ap, rs->regions, rs->max_message_bytes, rs->rank, rs->world);
+        if (rc) return rc;
+        for (int r = 0; r < rs->world; ++r) prs.rs.region[r] = ap.region[r];
+        prs.rs.epoch = ap.epoch;
+        prs.rs.src_stride = ap.src_stride;
+        prs.rs.parity_stride = ap.parity_stride;
+        prs.rs.rank = rs->rank;
+        prs.rs.world = rs->world;
+        return launch_cluster_gemm_rs(fmt, is_bf16 != 0, bpad, xmap, wmap, prs, n_tiles, (cudaStream_t)stream);
+    }
     return launch_cluster_gemm(fmt, is_bf16 != 0, bpad, xmap, wmap, p, n_tiles, (cudaStream_t)stream);
 }
+}  // namespace
 
 // ------------------------------------------------------------------------------------------------ glue ops
 int b200_add_rmsnorm(const void* x, void* residual, const void* gamma, void* y, int is_bf16, int rows, int hidden,
@@ -1099,8 +1158,21 @@ int b200_peer_allreduce(const void* in, void* out, size_t bytes, int is_bf16, vo
     return launched("peer_allreduce_kernel");
 }
 
+namespace {
+int allreduce_norm_impl(const void* in, void* residual, const void* gamma, void* y, int is_bf16, int rows, int hidden,
+                        float eps, void* const* regions, size_t max_message_bytes, int rank, int world, int pushed, void* stream);
+}
 int b200_peer_allreduce_norm(const void* in, void* residual, const void* gamma, void* y, int is_bf16, int rows, int hidden,
                              float eps, void* const* regions, size_t max_message_bytes, int rank, int world, void* stream) {
+    return allreduce_norm_impl(in, residual, gamma, y, is_bf16, rows, hidden, eps, regions, max_message_bytes, rank, world, 0, stream);
+}
+int b200_peer_gather_norm(const void* in, void* residual, const void* gamma, void* y, int is_bf16, int rows, int hidden,
+                          float eps, void* const* regions, size_t max_message_bytes, int rank, int world, void* stream) {
+    return allreduce_norm_impl(in, residual, gamma, y, is_bf16, rows, hidden, eps, regions, max_message_bytes, rank, world, 1, stream);
+}
+namespace {
+int allreduce_norm_impl(const void* in, void* residual, const void* gamma, void* y, int is_bf16, int rows, int hidden,
+                        float eps, void* const* regions, size_t max_message_bytes, int rank, int world, int pushed, void* stream) {
     ARG_CHECK(in && residual && gamma && y && regions, "peer_allreduce_norm: null pointer");
     ARG_CHECK(world >= 2 && world <= kArMaxWorld && rank >= 0 && rank < world, "peer_allreduce_norm: bad rank/world %d/%d", rank, world);
     ARG_CHECK(rows > 0 && rows <= 65535, "peer_allreduce_norm: rows %d unsupported", rows);
@@ -1110,7 +1182,7 @@ int b200_peer_allreduce_norm(const void* in, void* residual, const void* gamma, 
     if (g_rec) {
         std::vector<void*> regs(regions, regions + world);
         return rec_call([=](void* st) {
-            return b200_peer_allreduce_norm(in, residual, gamma, y, is_bf16, rows, hidden, eps, regs.data(), max_message_bytes, rank, world, st);
+            return allreduce_norm_impl(in, residual, gamma, y, is_bf16, rows, hidden, eps, regs.data(), max_message_bytes, rank, world, pushed, st);
         });
     }
     PeerArParams p{};
@@ -1123,6 +1195,7 @@ int b200_peer_allreduce_norm(const void* in, void* residual, const void* gamma, 
     p.rows = rows;
     p.hidden = hidden;
     p.eps = eps;
+    p.pushed = pushed;
     const size_t smem = (size_t)hidden * sizeof(float) + (size_t)(hidden / 8 / world) * 16;
     const bool pdl = g_pdl.load() != 0;
     if (is_bf16)
@@ -1131,6 +1204,7 @@ int b200_peer_allreduce_norm(const void* in, void* residual, const void* gamma, 
         CUDA_CHECK(launch_ex(peer_allreduce_norm_kernel<__half>, dim3(rows), dim3(kArThreads), smem, (cudaStream_t)stream, pdl, p));
     return launched("peer_allreduce_norm_kernel");
 }
+}  // namespace
 
 int b200_peer_argmax(const void* logits, int is_bf16, int rows, int vocab_local, int vocab_total, int32_t* out,
                      void* const* regions, size_t max_message_bytes, int rank, int world, void* stream) {

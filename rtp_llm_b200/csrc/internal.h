@@ -11,6 +11,7 @@
 
 namespace b200 {
 struct GemmParams;
+struct GemmParamsRs;
 struct ProgOp;
 }  // namespace b200
 
@@ -36,6 +37,9 @@ extern thread_local unsigned long long* g_ftrace_next;   // developer: fine time
 // gemm_cluster.cu: the one-kernel-per-GEMM path (cluster split-K merge); FP16 weights and batches > 64 use it
 int launch_cluster_gemm(int fmt, bool bf16, int bpad, const CUtensorMap& xmap, const CUtensorMap& wmap,
                         const b200::GemmParams& p, int n_tiles, cudaStream_t st);
+// gemm_cluster_rs.cu: the same kernels with the TP reduce-scatter push in the epilogue (p.rs filled in)
+int launch_cluster_gemm_rs(int fmt, bool bf16, int bpad, const CUtensorMap& xmap, const CUtensorMap& wmap,
+                           const b200::GemmParamsRs& p, int n_tiles, cudaStream_t st);
 
 // segment_*.cu: the persistent stream-K kernel (csrc/decode_program.cuh). qfmt: B200_FMT_INT8 / B200_FMT_INT4.
 // grid == 0 asks for the co-resident grid size only (written to *grid_out).

@@ -33,6 +33,7 @@ struct PeerArParams {
     void* y;                        // [rows][hidden] normalised output
     int rows, hidden;
     float eps;
+    int pushed;                     // 1: the producing GEMM already pushed the reduce-scatter words (b200_wo_gemm_rs): skip phase 1
     // vocab-parallel greedy sampling (peer_argmax_kernel)
     const void* logits;             // [rows][vocab_local]
     int32_t* token_out;             // [rows]
@@ -227,11 +228,14 @@ __global__ void __launch_bounds__(kArThreads) peer_allreduce_norm_kernel(const P
     const int row = blockIdx.x, C = p.hidden / 8, Cs = C / p.world;
     const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(p.epoch) + 1;
     const uint4* src = reinterpret_cast<const uint4*>(p.in) + (size_t)row * C;
-    // 1) reduce-scatter: chunk c of my row goes to its owner's slot [src = rank]
-    for (int c = threadIdx.x; c < C; c += kArThreads) {
-        const int owner = c / Cs;
-        if (owner != p.rank)
-            push_chunk(ar_area(p, owner, epoch, 0) + (size_t)p.rank * p.src_stride + ((size_t)row * Cs + (c - owner * Cs)) * 32, src[c], epoch);
+    // 1) reduce-scatter: chunk c of my row goes to its owner's slot [src = rank] -- unless the GEMM that produced the row
+    //    already pushed it from its epilogue (b200_wo_gemm_rs: same slot layout, same epoch, same rounded bits)
+    if (!p.pushed) {
+        for (int c = threadIdx.x; c < C; c += kArThreads) {
+            const int owner = c / Cs;
+            if (owner != p.rank)
+                push_chunk(ar_area(p, owner, epoch, 0) + (size_t)p.rank * p.src_stride + ((size_t)row * Cs + (c - owner * Cs)) * 32, src[c], epoch);
+        }
     }
     // 2) reduce my slice in rank order, round to T, keep it and push it to every peer's all-gather slot [src = rank]
     for (int cs = threadIdx.x; cs < Cs; cs += kArThreads) {

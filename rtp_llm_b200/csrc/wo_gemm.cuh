@@ -79,6 +79,17 @@ __host__ __device__ constexpr int gemm_smem_bytes(int fmt, int bpad, int var) {
     return gemm_x_stages(bpad) * gemm_x_stage_bytes(bpad) + gemm_w_stages(fmt, bpad, var) * gemm_w_bytes(fmt) + kGemmSmemMisc;
 }
 
+// Row-parallel GEMM under tensor parallelism (b200_wo_gemm_rs): the epilogue pushes every output element that another rank
+// owns straight into that rank's reduce-scatter slot over NVLink, as LL words {two elements, epoch} in the layout
+// peer_allreduce_norm_kernel polls (peer_allreduce.cuh: area 0, slot [src = rank][row][chunk of the owner's slice]); the
+// columns this rank owns are stored to y as usual. world == 0: off.
+struct RsPush {
+    uint8_t* region[8];                              // region[r]: base of rank r's peer-visible region
+    const uint32_t* epoch;                           // device-side call counter of the communicator (read, not advanced)
+    unsigned long long src_stride, parity_stride;
+    int rank, world;
+};
+
 struct GemmParams {
     const uint8_t* w_blob;   // int4 / int8: pre-tiled blobs [n_tiles][k_blocks][block bytes]; f16: unused (tensor map)
     const void* col_scale;   // int8: per-column scale [N] (T); else null
@@ -94,6 +105,20 @@ struct GemmParams {
     int cluster_reduce;      // 1: the nsplit CTAs of a tile form a cluster (1,nsplit,1) and merge through DSMEM
     long long* trace;        // developer timeline (tools/gemm_trace.py); null in production
     int dbg;                 // developer experiments (env B200_GEMM_DBG): 1 no math, 2 no TMEM store, 4 no MMA; 0 in production
+};
+
+// The VAR == 1 kernels (gemm_cluster_rs.cu) take the descriptor of the reduce-scatter push after the common parameters; the
+// plain kernels keep the smaller struct (a larger parameter block cost them a spilled register).
+struct GemmParamsRs : GemmParams {
+    RsPush rs;
+};
+template <int VAR>
+struct GemmParamsOf {
+    using type = GemmParams;
+};
+template <>
+struct GemmParamsOf<1> {
+    using type = GemmParamsRs;
 };
 
 // ---- int4 -> fp16/bf16 pairs.  Nibble p of a word holds u = q_s + 8; p<4 <-> k = 2p, p>=4 <-> k = 2(p-4)+1, so each
@@ -173,6 +198,36 @@ struct Dequant8<__nv_bfloat16> {
     }
 };
 
+// One thread's share of the reduce-scatter push: the thread owns output column n (fixed) of every batch row it visits.
+struct RsLane {
+    uint8_t* remote;         // slot address of (row 0, the word holding columns n, n+1) in the owner's region; null: this rank owns n
+    uint32_t row_bytes;      // bytes between consecutive batch rows in that slot
+    uint32_t epoch;
+};
+__device__ __forceinline__ RsLane rs_lane(const GemmParamsRs& p, int n) {
+    RsLane l;
+    l.epoch = *reinterpret_cast<const volatile uint32_t*>(p.rs.epoch) + 1u;   // the call the follow-up gather+norm kernel will run as
+    const int Cs = p.N / 8 / p.rs.world, c = n >> 3, owner = c / Cs;
+    l.row_bytes = (uint32_t)Cs * 32u;
+    l.remote = owner == p.rs.rank ? nullptr
+                                  : p.rs.region[owner] + (size_t)(l.epoch & 1u) * p.rs.parity_stride + (size_t)p.rs.rank * p.rs.src_stride +
+                                        (size_t)(c - owner * Cs) * 32 + ((n & 7) >> 1) * 8;
+    return l;
+}
+// v = this lane's value for (row b, column n); lanes 2i / 2i+1 hold adjacent columns: the even lane emits the pair.
+// Must be called by all 32 lanes of the warp with the same b.
+template <typename T>
+__device__ __forceinline__ void rs_emit(const GemmParams& p, const RsLane& l, int b, int n, float v, int lane) {
+    const float hi = __shfl_down_sync(0xffffffffu, v, 1);
+    if (lane & 1) return;
+    const uint32_t data = pack2<T>(v, hi);
+    if (l.remote == nullptr) {
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<T*>(p.y) + (size_t)b * p.N + n) = data;
+    } else {
+        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(l.remote + (size_t)b * l.row_bytes), "r"(data), "r"(l.epoch) : "memory");
+    }
+}
+
 template <typename T>
 struct Pair;
 template <>
@@ -206,7 +261,8 @@ struct Pair<__nv_bfloat16> {
 
 template <int FMT, typename T, int BPAD, int VAR>
 __global__ void __launch_bounds__(gemm_threads(VAR), gemm_min_ctas(FMT, BPAD, VAR))
-wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap w_map, const GemmParams p) {
+wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap w_map,
+               const typename GemmParamsOf<VAR>::type p) {
     constexpr int WS = gemm_w_stages(FMT, BPAD, VAR);      // weight ring depth
     constexpr int XS = gemm_x_stages(BPAD);                // activation ring depth
     constexpr int NDQ_WARPS = gemm_ndq_warps(VAR);
@@ -555,6 +611,8 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
             }
         };
         if (p.nsplit == 1) {
+            RsLane rsl{};
+            if constexpr (VAR == 1) rsl = rs_lane(p, n);
             for (int sl = kce; sl < SLICES; sl += KCS) {
                 float v[16];
                 load_acc(sl, v);
@@ -562,7 +620,9 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
                 for (int j = 0; j < 16; ++j) {
                     const int b = sl * 16 + j;
                     if (p.silu_mul) fin[b * kGemmTileN + row] = fmaf(v[j], cscale, bias);
-                    else if (n_ok && b < p.B) yp[(size_t)b * p.N + n] = from_f32<T>(fmaf(v[j], cscale, bias));
+                    else if constexpr (VAR == 1) {
+                        if (b < p.B) rs_emit<T>(p, rsl, b, n, fmaf(v[j], cscale, bias), lane);    // N % 128 == 0 in this mode
+                    } else if (n_ok && b < p.B) yp[(size_t)b * p.N + n] = from_f32<T>(fmaf(v[j], cscale, bias));
                 }
             }
         } else if (p.cluster_reduce) {
@@ -642,6 +702,8 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
             }
             const float* red = reinterpret_cast<const float*>(xring);
             T* yp = reinterpret_cast<T*>(p.y);
+            RsLane rsl{};
+            if constexpr (VAR == 1) rsl = rs_lane(p, n);
             // CTA `rank` owns batch columns rank, rank+S, ...; fixed summation order sp = 0..S-1 (deterministic)
             for (int b = rank + lane_grp * S; b < p.B; b += S * (NDQ_THREADS / kGemmTileN)) {
                 const uint32_t laddr = smem_u32(red + b * kGemmTileN + row);
@@ -652,6 +714,7 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
 #pragma unroll
                 for (int sp = 0; sp < 8; ++sp) acc += part[sp];
                 if (p.silu_mul) reinterpret_cast<float*>(wring)[b * kGemmTileN + row] = fmaf(acc, cscale, bias);
+                else if constexpr (VAR == 1) rs_emit<T>(p, rsl, b, n, fmaf(acc, cscale, bias), lane);
                 else if (n_ok) yp[(size_t)b * p.N + n] = from_f32<T>(fmaf(acc, cscale, bias));
             }
         }

@@ -63,7 +63,8 @@ class DecodeStep:
 
     def __init__(self, cfg: ModelConfig, batch: int, ctx: int, device: torch.device, tp_rank: int = 0, tp_size: int = 1,
                  dtype=torch.float16, seed: int = 0, keep_reference: bool = False, ragged: bool = False,
-                 pdl: bool = False, comm=None, fuse_silu: bool = True, fuse_ar_norm: bool = True, fuse_rope: Optional[bool] = None):
+                 pdl: bool = False, comm=None, fuse_silu: bool = True, fuse_ar_norm: bool = True, fuse_rope: Optional[bool] = None,
+                 fuse_gemm_rs: Optional[bool] = None):
         assert cfg.head_num % tp_size == 0 and cfg.inter % tp_size == 0
         self.cfg, self.B, self.ctx, self.dev, self.dtype = cfg, batch, ctx, device, dtype
         self.tp_rank, self.tp_size, self.comm, self.pdl = tp_rank, tp_size, comm, pdl
@@ -79,6 +80,13 @@ class DecodeStep:
         self.ref: Dict[str, list] = {} if keep_reference else None
         self.fuse_silu = fuse_silu and self.inter % 64 == 0
         self.fuse_ar_norm = fuse_ar_norm
+        # row-parallel GEMM + reduce-scatter in one kernel (b200_wo_gemm_rs), then gather + residual + norm (b200_peer_gather_norm):
+        # only with the peer communicator and the fused all-reduce+norm; B200_FUSE_GEMM_RS=0 turns it off (A/B runs)
+        import os as _os
+        if fuse_gemm_rs is None:
+            fuse_gemm_rs = _os.environ.get("B200_FUSE_GEMM_RS", "1") == "1"
+        self.fuse_gemm_rs = (bool(fuse_gemm_rs) and fuse_ar_norm and tp_size > 1 and hasattr(comm, "gemm_rs")
+                             and comm.gemm_rs_supported(batch, cfg.hidden))
         # RoPE + K/V append inside the attention kernel (b200_paged_decode_attn_rope): bit-identical, one launch less per layer,
         # but measured 0.4 % SLOWER at the headline config (same box A/B, profiles/r02_fuse_rope_ab.txt): under PDL the stand-alone
         # rope kernel hides behind its neighbours while the fused prologue sits on the attention kernel's critical path.
@@ -254,9 +262,20 @@ class DecodeStep:
         if self.tp_size > 1:
             self.comm.all_reduce(t)
 
+    def _row_gemm(self, x, w):
+        """self.proj = x . w for a row-parallel weight (o, w2). Fused form (b200_wo_gemm_rs): the GEMM epilogue pushes the
+        reduce-scatter words over NVLink; the _ar_norm() that follows then only reduces / gathers / normalises."""
+        if self.fuse_gemm_rs and hasattr(self.comm, "gemm_rs"):    # (bench.py swaps the communicator for its NCCL parity arm)
+            self.comm.gemm_rs(x, w, self.gemm_ws, self.proj, pdl=self.pdl)
+        else:
+            ops.wo_gemm(x, w, self.gemm_ws, out=self.proj, pdl=self.pdl)
+
     def _ar_norm(self, t, gamma):
         """[TP all-reduce of the row-parallel GEMM output t] + residual add + RMSNorm -> self.x. With the peer communicator the
         three steps are ONE kernel (b200_peer_allreduce_norm); otherwise all-reduce and fused_add_rmsnorm run separately."""
+        if self.fuse_gemm_rs and hasattr(self.comm, "gemm_rs"):      # t came out of _row_gemm(): its scatter phase is already on the wire
+            self.comm.gather_norm(t, self.resid, gamma, self.cfg.eps, self.x)
+            return
         if self.tp_size > 1:
             fused = getattr(self.comm, "all_reduce_norm", None)
             if self.fuse_ar_norm and fused is not None and fused(t, self.resid, gamma, self.cfg.eps, self.x):
@@ -284,14 +303,14 @@ class DecodeStep:
             else:
                 ops.rope_append(self.qkv, L["kv"], self.page_list, self.seq_lens, self.Hq, cfg.rope_base, q_out=self.q)
                 ops.paged_decode_attn(self.q, L["kv"], self.page_list, self.seq_lens, self.ctx, self.attn_ws, out=self.attn)
-            ops.wo_gemm(self.attn, L["o"], self.gemm_ws, out=self.proj, pdl=self.pdl)
+            self._row_gemm(self.attn, L["o"])
             self._ar_norm(self.proj, L["ln2"])
             if self.fuse_silu:     # SiLU(gate)*up in the GEMM epilogue (gate/up columns interleaved at load time)
                 ops.wo_gemm(self.x, L["w13"], self.gemm_ws, out=self.act, pdl=self.pdl, silu_mul=True)
             else:
                 ops.wo_gemm(self.x, L["w13"], self.gemm_ws, out=self.gu, pdl=self.pdl)
                 ops.silu_and_mul(self.gu, out=self.act)
-            ops.wo_gemm(self.act, L["w2"], self.gemm_ws, out=self.proj, pdl=self.pdl)
+            self._row_gemm(self.act, L["w2"])
         self._ar_norm(self.proj, self.final_ln)
         ops.wo_gemm(self.x, self.lm_head, self.gemm_ws, out=self.logits, pdl=self.pdl)
         if self.tp_size == 1:

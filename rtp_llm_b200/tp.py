@@ -77,6 +77,30 @@ class PeerComm(NcclComm):
                                                       torch.cuda.current_stream().cuda_stream), "b200_peer_allreduce_norm")
         return True
 
+    def gemm_rs_supported(self, rows: int, hidden: int, elem_size: int = 2) -> bool:
+        return (rows * hidden * elem_size <= self.MAX_MESSAGE and hidden % (8 * self.world) == 0 and hidden % 128 == 0
+                and hidden <= 8192 and rows <= 128)
+
+    def gemm_rs(self, x: torch.Tensor, w, workspace: torch.Tensor, out: torch.Tensor, pdl: bool = False, bias=None) -> None:
+        """Row-parallel GEMM whose epilogue pushes the reduce-scatter words to their owners (b200_wo_gemm_rs); must be
+        followed by gather_norm() on `out`."""
+        from . import _lib
+        B, K = x.shape
+        _lib.check(self._lib.b200_wo_gemm_rs(w.fmt, 1 if x.dtype == torch.bfloat16 else 0, x.data_ptr(), B, K, w.N, w.data.data_ptr(),
+                                             w.col_scale.data_ptr() if w.col_scale is not None else None,
+                                             bias.data_ptr() if bias is not None else None, out.data_ptr(), workspace.data_ptr(),
+                                             workspace.numel(), _lib.B200_GEMM_PDL if pdl else 0, self._regions, self.MAX_MESSAGE,
+                                             self.rank, self.world, torch.cuda.current_stream().cuda_stream), "b200_wo_gemm_rs")
+
+    def gather_norm(self, t: torch.Tensor, residual: torch.Tensor, gamma: torch.Tensor, eps: float, out: torch.Tensor) -> None:
+        """Second half of gemm_rs(): reduce own slice + all-gather + residual add + RMSNorm (b200_peer_gather_norm)."""
+        from . import _lib
+        rows, hidden = t.shape
+        _lib.check(self._lib.b200_peer_gather_norm(t.data_ptr(), residual.data_ptr(), gamma.data_ptr(), out.data_ptr(),
+                                                   1 if t.dtype == torch.bfloat16 else 0, rows, hidden, eps, self._regions,
+                                                   self.MAX_MESSAGE, self.rank, self.world,
+                                                   torch.cuda.current_stream().cuda_stream), "b200_peer_gather_norm")
+
     def argmax(self, logits: torch.Tensor, vocab_total: int, out: torch.Tensor) -> None:
         """Greedy token over the vocab-split logits (rank r holds columns [r*V_local, (r+1)*V_local))."""
         from . import _lib

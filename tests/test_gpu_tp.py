@@ -36,6 +36,9 @@ def test_peer_collectives_match_torch():
     _torchrun("tp_collectives_check.py", _world())
 
 
+@pytest.mark.parametrize("gemm_rs", ["1", "0"], ids=["gemm_rs", "gemm_then_allreduce"])
 @pytest.mark.parametrize("program", ["0", "1"], ids=["op_by_op", "program"])
-def test_tp_tiny_step_matches_unsharded_oracle(program):
-    _torchrun("tp_check.py", _world(), env={"TP_PROGRAM": program})
+def test_tp_tiny_step_matches_unsharded_oracle(program, gemm_rs):
+    """gemm_rs=1 (default): row-parallel GEMMs push their reduce-scatter words from the epilogue (b200_wo_gemm_rs) and
+    b200_peer_gather_norm finishes the exchange; gemm_rs=0: b200_wo_gemm followed by b200_peer_allreduce_norm."""
+    _torchrun("tp_check.py", _world(), env={"TP_PROGRAM": program, "B200_FUSE_GEMM_RS": gemm_rs})
