@@ -77,6 +77,32 @@ class B200Error(RuntimeError):
     rtp_llm/cpp/utils/AssertUtils.h:18-27)."""
 
 
+def _rebuild_if_stale() -> None:
+    """The library exists: make sure it was built from the sources next to it (content digest recorded by build.py). A stale
+    library is rebuilt under a file lock (several ranks may get here at once); if that is impossible the load fails loudly --
+    an edited kernel must never run against an old binary."""
+    if os.environ.get("B200_LIB_PATH"):
+        return                                    # an explicitly chosen library (developer builds) is taken as it is
+    from . import build as _build
+    try:
+        if _build.stamp_matches():
+            return
+    except OSError:
+        return                                    # sources not shipped with the library: nothing to compare against
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            if not _build.stamp_matches():        # (another process may have rebuilt it while we waited)
+                try:
+                    _build.build(force=True)
+                except Exception as e:  # noqa: BLE001
+                    raise B200Error(f"{LIB_PATH} is older than the sources in {os.path.dirname(LIB_PATH)}/csrc and could not be "
+                                    f"rebuilt ({e}): run `python -m rtp_llm_b200.build`") from e
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
+
+
 def load() -> ctypes.CDLL:
     global _lib
     if _lib is None:
@@ -88,6 +114,8 @@ def load() -> ctypes.CDLL:
             except Exception as e:  # noqa: BLE001
                 raise B200Error(f"{LIB_PATH} is missing and could not be built ({e}): run `python -m rtp_llm_b200.build` "
                                 "(nvcc, sm_100a). There is no fallback path.") from e
+        else:
+            _rebuild_if_stale()
         lib = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the header and the library ever diverge

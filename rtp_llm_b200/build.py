@@ -38,8 +38,36 @@ def _stale() -> bool:
     return _newer(LIB, _deps() + [os.path.join(CSRC, s) for s in SOURCES])
 
 
+STAMP = LIB + ".stamp"
+
+
+def source_digest() -> str:
+    """sha256 over every source / header / flag the library is built from. build() records it next to the .so; _lib.load()
+    compares it, so an edited kernel can never run against an old library -- by CONTENT, because file times do not survive
+    the copy to the GPU box."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for p in sorted(_deps()[:-1] + [os.path.join(CSRC, s) for s in SOURCES]):     # (build.py itself is not an input of nvcc)
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def stamp_matches() -> bool:
+    """True when the library on disk was built from the sources on disk (or carries no stamp: a library of unknown origin
+    is used as it is, as before)."""
+    if not os.path.exists(STAMP):
+        return True
+    with open(STAMP) as f:
+        return f.read().strip() == source_digest()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+    if not force and not _stale() and stamp_matches():
+        if not os.path.exists(STAMP):
+            with open(STAMP, "w") as f:
+                f.write(source_digest())
         return LIB
     from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -54,7 +82,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return obj
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"])
+    subprocess.check_call([nvcc, "-shared", "-o", LIB + ".tmp"] + objs + ["-lcudart"])
+    os.replace(LIB + ".tmp", LIB)             # atomic: another process never maps a half-written library
+    with open(STAMP, "w") as f:
+        f.write(source_digest())
     return LIB
 
 

@@ -141,3 +141,18 @@ def test_gate_up_interleave_order():
     got = ops.interleave_gate_up(packed, inter, packed_int4=True)
     got_nib = torch.stack([got & 0xF, got >> 4], dim=-1).reshape(2, -1)
     assert torch.equal(got_nib, nib.index_select(-1, order))
+
+
+def test_library_staleness_is_judged_by_content(tmp_path, monkeypatch):
+    """build.py records a digest of every source the library was built from; _lib.load() compares it (an edited
+    kernel must never run against an old libb200_decode.so; file times do not survive the copy to the GPU box)."""
+    from rtp_llm_b200 import build as b
+    d = b.source_digest()
+    assert len(d) == 64 and d == b.source_digest()
+    stamp = tmp_path / "lib.stamp"
+    monkeypatch.setattr(b, "STAMP", str(stamp))
+    assert b.stamp_matches()                      # no stamp: a library of unknown origin is used as it is
+    stamp.write_text(d)
+    assert b.stamp_matches()
+    stamp.write_text("0" * 64)
+    assert not b.stamp_matches()                  # sources changed since the build -> load() rebuilds (or fails loudly)
