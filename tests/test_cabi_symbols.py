@@ -37,6 +37,33 @@ def test_argument_errors_are_reported_not_crashed():
     assert lib.b200_wo_gemm_workspace_bytes(32, 4096, 4096) >= 16384
 
 
+def test_argument_errors_of_the_round2_entry_points():
+    """Validation happens on the host before any CUDA call: checkable without a GPU. Mirrors the reference ops' behaviour of
+    raising on bad shapes (XQAAttnOp.cc:62-70 RTP_LLM_CHECK_WITH_INFO) instead of launching."""
+    import ctypes
+    lib = _lib.load()
+    buf = (ctypes.c_uint8 * 4096)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    regs = (ctypes.c_void_p * 8)(*([p.value] * 8))
+    # 8-bit group-wise blobs: 16384 payload bytes + 512 bytes of scales / zero*scale per (128 x 128) block
+    assert lib.b200_wo_gemm_packed_bytes(_lib.B200_FMT_INT8G, 256, 256) == 2 * 2 * 16896
+    assert lib.b200_wo_gemm_packed_bytes(7, 256, 256) == 0                                    # unknown format
+    assert lib.b200_pack_w8g(p, p, p, 256, 256, 64, p, None) == -1 and b"group" in lib.b200_last_error()
+    assert lib.b200_pack_w8g(p, p, p, 100, 256, 128, p, None) == -1 and b"multiple of 128" in lib.b200_last_error()
+    # GEMM + reduce-scatter: world / shape limits
+    args = (_lib.B200_FMT_INT4, 0, p, 32, 512, 4096, p, None, None, p, p, 4096, 0)
+    assert lib.b200_wo_gemm_rs(*args, regs, 1 << 19, 0, 1, None) == -1 and b"rank/world" in lib.b200_last_error()
+    assert lib.b200_wo_gemm_rs(*args, regs, 1 << 10, 0, 2, None) == -1 and b"exceeds the region" in lib.b200_last_error()
+    bad_n = (_lib.B200_FMT_INT4, 0, p, 32, 512, 4160, p, None, None, p, p, 4096, 0)
+    assert lib.b200_wo_gemm_rs(*bad_n, regs, 1 << 19, 0, 2, None) == -1 and b"multiple of 128" in lib.b200_last_error()
+    silu = args[:-1] + (_lib.B200_GEMM_SILU_MUL,)
+    assert lib.b200_wo_gemm_rs(*silu, regs, 1 << 19, 0, 2, None) == -1 and b"SILU_MUL" in lib.b200_last_error()
+    assert lib.b200_wo_gemm(9, 0, p, 32, 512, 4096, p, None, None, p, p, 4096, 0, None) == -1 and b"unknown weight format" in lib.b200_last_error()
+    assert lib.b200_wo_gemm(_lib.B200_FMT_INT8, 0, p, 32, 512, 4096, p, None, None, p, p, 4096, 0, None) == -1 and b"col_scale" in lib.b200_last_error()
+    # the second half of the exchange shares the all-reduce+norm checks
+    assert lib.b200_peer_gather_norm(p, p, p, p, 0, 32, 4100, 1e-5, regs, 1 << 19, 0, 2, None) == -1 and b"hidden" in lib.b200_last_error()
+
+
 def test_sass_uses_the_blackwell_paths():
     """The built library must contain tcgen05 MMA, TMEM ld/st and TMA instructions (SASS mnemonics of B200_PROFILING.md)."""
     import shutil
