@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""GPU bring-up probe (developer tool, run under gpurun): exercises every kernel against the oracle / the naive GPU
+"""GPU parity cases (test infrastructure: imported by tests/test_gpu_parity.py, also runnable by hand under gpurun): exercises every kernel against the oracle / the naive GPU
 checkers and prints a compact diagnosis per case instead of stopping at the first failure."""
 import math
 import os

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 from oracle import oracle as orc  # noqa: E402
 from rtp_llm_b200 import ops  # noqa: E402
 from rtp_llm_b200._lib import B200_FMT_F16, B200_FMT_INT4, B200_FMT_INT8, B200_FMT_INT8G  # noqa: E402
-from tools import gpu_probe as probe  # noqa: E402
+from tests import gpu_probe as probe  # noqa: E402
 
 
 def _run(fn, *a, **k):
