@@ -11,6 +11,7 @@
 // (cpp/model_utils/AttentionConfig.h:24-85, bindings/OpDefs.h:29-51,281-327, bindings/ParamsBase.h:8-22); standalone they are the
 // minimal mirrors declared here (same member names). Only torch tensors and plain ints cross into include/b200_decode_ops.h.
 #include <ATen/cuda/CUDAContext.h>
+#include <cuda_runtime.h>
 #include <torch/extension.h>
 
 #include <optional>
@@ -195,7 +196,94 @@ private:
     std::optional<torch::Tensor> col_scale_, bias_;
 };
 
+// ---- glue ops under the reference's own names and argument lists (registerBasicCudaOps, cuda/RegisterBaseBindings.hpp:45-160;
+// prototypes 3rdparty/flashinfer/flashinfer.h:21-31, common/FusedQKRmsNorm.cc:17-25, common/RtpEmbeddingLookup.cc:14-19): a model file
+// that calls rtp_llm_ops.rmsnorm / fused_add_rmsnorm / silu_and_mul / fused_qk_rmsnorm / embedding runs unchanged on this plugin.
+// cuda_stream: the raw stream handle the callers pass (torch.cuda.current_stream().cuda_stream, modules/base/cuda/norm.py:22); 0 = current.
+static void* stream_arg(int64_t cuda_stream) { return cuda_stream ? reinterpret_cast<void*>(cuda_stream) : cur_stream(); }
+static void check_rows(const torch::Tensor& t, const char* what) {
+    B200_CHECK(t.defined() && t.is_cuda() && t.is_contiguous() && t.dim() == 2, std::string(what) + ": expected a contiguous 2-D CUDA tensor");
+    B200_CHECK(t.scalar_type() == torch::kFloat16 || t.scalar_type() == torch::kBFloat16, std::string(what) + ": expected fp16 / bf16");
+}
+
+static void rmsnorm(torch::Tensor& output, torch::Tensor& input, torch::Tensor& weight, double eps, int64_t cuda_stream) {
+    check_rows(input, "rmsnorm input");
+    check_rows(output, "rmsnorm output");
+    B200_CHECK(output.sizes() == input.sizes() && weight.numel() == input.size(1) && weight.scalar_type() == input.scalar_type(),
+               "rmsnorm: shape / dtype mismatch");
+    check_rc(b200_add_rmsnorm(input.data_ptr(), nullptr, weight.data_ptr(), output.data_ptr(), input.scalar_type() == torch::kBFloat16,
+                              (int)input.size(0), (int)input.size(1), (float)eps, stream_arg(cuda_stream)),
+             "b200_add_rmsnorm");
+}
+
+// flashinfer semantics: residual <- input + residual (rounded to the tensor type), input <- rmsnorm(unrounded sum) * weight
+static void fused_add_rmsnorm(torch::Tensor& input, torch::Tensor& residual, torch::Tensor& weight, double eps, int64_t cuda_stream) {
+    check_rows(input, "fused_add_rmsnorm input");
+    check_rows(residual, "fused_add_rmsnorm residual");
+    B200_CHECK(residual.sizes() == input.sizes() && weight.numel() == input.size(1) && weight.scalar_type() == input.scalar_type() &&
+                   residual.scalar_type() == input.scalar_type(),
+               "fused_add_rmsnorm: shape / dtype mismatch");
+    torch::Tensor out = torch::empty_like(input);      // the kernel's input and output do not alias; the result is copied back in stream order
+    void* st = stream_arg(cuda_stream);
+    check_rc(b200_add_rmsnorm(input.data_ptr(), residual.data_ptr(), weight.data_ptr(), out.data_ptr(),
+                              input.scalar_type() == torch::kBFloat16, (int)input.size(0), (int)input.size(1), (float)eps, st),
+             "b200_add_rmsnorm");
+    B200_CHECK(cudaMemcpyAsync(input.data_ptr(), out.data_ptr(), (size_t)input.numel() * input.element_size(), cudaMemcpyDeviceToDevice,
+                               reinterpret_cast<cudaStream_t>(st)) == cudaSuccess,
+               "fused_add_rmsnorm: copy back failed");
+}
+
+static void silu_and_mul(torch::Tensor& output, torch::Tensor& input, int64_t cuda_stream) {
+    check_rows(input, "silu_and_mul input");
+    check_rows(output, "silu_and_mul output");
+    B200_CHECK(input.size(1) % 2 == 0 && output.size(0) == input.size(0) && output.size(1) * 2 == input.size(1) &&
+                   output.scalar_type() == input.scalar_type(),
+               "silu_and_mul: expected input [rows, 2*inter] (gate | up) and output [rows, inter]");
+    check_rc(b200_silu_and_mul(input.data_ptr(), output.data_ptr(), input.scalar_type() == torch::kBFloat16, (int)input.size(0),
+                               (int)(input.size(1) / 2), stream_arg(cuda_stream)),
+             "b200_silu_and_mul");
+}
+
+// in place on IO [m, n] = rows of q heads | k heads | v heads; q_group_num / k_group_num = head counts, norm_size = head size
+static void fused_qk_rmsnorm(torch::Tensor& IO, torch::Tensor& q_gamma, torch::Tensor& k_gamma, double layernorm_eps, int64_t q_group_num,
+                             int64_t k_group_num, int64_t m, int64_t n, int64_t norm_size) {
+    check_rows(IO, "fused_qk_rmsnorm IO");
+    B200_CHECK(IO.size(0) == m && IO.size(1) == n && n == (q_group_num + 2 * k_group_num) * norm_size,
+               "fused_qk_rmsnorm: n must equal (q_group_num + 2 * k_group_num) * norm_size");
+    B200_CHECK(q_gamma.numel() == norm_size && k_gamma.numel() == norm_size && q_gamma.scalar_type() == IO.scalar_type() &&
+                   k_gamma.scalar_type() == IO.scalar_type(),
+               "fused_qk_rmsnorm: gamma shape / dtype mismatch");
+    check_rc(b200_qk_rmsnorm(IO.data_ptr(), q_gamma.data_ptr(), k_gamma.data_ptr(), nullptr, nullptr, IO.scalar_type() == torch::kBFloat16,
+                             (int)m, (int)q_group_num, (int)k_group_num, (int)norm_size, (float)layernorm_eps, cur_stream()),
+             "b200_qk_rmsnorm");
+}
+
+static void embedding(torch::Tensor& output, torch::Tensor& input, torch::Tensor& weight, std::optional<torch::Tensor> position_ids,
+                      std::optional<torch::Tensor> token_type_ids, std::optional<torch::Tensor> text_tokens_mask) {
+    auto given = [](const std::optional<torch::Tensor>& t) { return t.has_value() && t->defined() && t->numel() > 0; };
+    B200_CHECK(!given(position_ids) && !given(token_type_ids) && !given(text_tokens_mask),
+               "embedding: position / token-type / mask tables are outside the decode path built here");
+    B200_CHECK(input.is_cuda() && input.is_contiguous() && input.dim() == 1 && input.scalar_type() == torch::kInt32,
+               "embedding: expected contiguous int32 token ids [tokens]");
+    check_rows(weight, "embedding weight");
+    check_rows(output, "embedding output");
+    B200_CHECK(output.size(0) == input.size(0) && output.size(1) == weight.size(1) && output.scalar_type() == weight.scalar_type(),
+               "embedding: output must be [tokens, hidden] of the weight's type");
+    check_rc(b200_embedding(input.data_ptr<int>(), weight.data_ptr(), output.data_ptr(), weight.scalar_type() == torch::kBFloat16,
+                            (int)input.size(0), (int)weight.size(1), cur_stream()),
+             "b200_embedding");
+}
+
 void registerPyModuleOps(pybind11::module& m) {
+    m.def("rmsnorm", &rmsnorm, "RMSNorm kernel", py::arg("output"), py::arg("input"), py::arg("weight"), py::arg("eps"),
+          py::arg("cuda_stream") = 0);
+    m.def("fused_add_rmsnorm", &fused_add_rmsnorm, "Fused Add RMSNorm kernel", py::arg("input"), py::arg("residual"), py::arg("weight"),
+          py::arg("eps"), py::arg("cuda_stream") = 0);
+    m.def("silu_and_mul", &silu_and_mul, "SiLU and Multiply kernel", py::arg("output"), py::arg("input"), py::arg("cuda_stream") = 0);
+    m.def("fused_qk_rmsnorm", &fused_qk_rmsnorm, "Fused QK RMSNorm kernel", py::arg("IO"), py::arg("q_gamma"), py::arg("k_gamma"),
+          py::arg("layernorm_eps"), py::arg("q_group_num"), py::arg("k_group_num"), py::arg("m"), py::arg("n"), py::arg("norm_size"));
+    m.def("embedding", &embedding, "Embedding lookup kernel", py::arg("output"), py::arg("input"), py::arg("weight"),
+          py::arg("position_ids") = py::none(), py::arg("token_type_ids") = py::none(), py::arg("text_tokens_mask") = py::none());
     py::class_<RopeConfig>(m, "RopeConfig").def(py::init<>()).def_readwrite("base", &RopeConfig::base);
     py::class_<AttentionConfigs>(m, "AttentionConfigs")
         .def(py::init<>())

@@ -33,6 +33,77 @@ def test_pybind_module_exposes_the_reference_surface():
     assert issubclass(ops.B200AttnParams, ops.ParamsBase)
 
 
+def test_pybind_glue_ops_carry_the_reference_names_and_arguments():
+    """registerBasicCudaOps (cuda/RegisterBaseBindings.hpp:45-160): same function names and keyword arguments, so a model file
+    written against rtp_llm_ops runs unchanged; bad inputs raise (RuntimeError) before anything is launched."""
+    ops = _load()
+    want = {"rmsnorm": ("output", "input", "weight", "eps", "cuda_stream"),
+            "fused_add_rmsnorm": ("input", "residual", "weight", "eps", "cuda_stream"),
+            "silu_and_mul": ("output", "input", "cuda_stream"),
+            "fused_qk_rmsnorm": ("IO", "q_gamma", "k_gamma", "layernorm_eps", "q_group_num", "k_group_num", "m", "n", "norm_size"),
+            "embedding": ("output", "input", "weight", "position_ids", "token_type_ids", "text_tokens_mask")}
+    for name, args in want.items():
+        doc = getattr(ops, name).__doc__
+        sig = doc[doc.index("(") + 1:doc.index(") ->")]
+        names = tuple(part.split(":")[0].strip() for part in sig.split(", ") if ":" in part)
+        assert names == args, (name, doc)
+    x = torch.zeros(2, 64, dtype=torch.float16)            # CPU tensors: rejected by the wrapper's checks
+    with pytest.raises(RuntimeError):
+        ops.rmsnorm(x.clone(), x, torch.ones(64, dtype=torch.float16), 1e-6)
+    with pytest.raises(RuntimeError):
+        ops.silu_and_mul(x.clone(), x)
+
+
+@pytest.mark.gpu
+def test_pybind_glue_ops_match_oracle():
+    from oracle import oracle as orc
+    ops = _load()
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(3)
+    bits = lambda t: t.cpu().contiguous().view(torch.int16).numpy().view(np.uint16)
+    for dtype in (torch.float16, torch.bfloat16):
+        is_bf16 = dtype == torch.bfloat16
+        tol = 2e-2 if is_bf16 else 4e-3
+        rows, hidden = 5, 1024
+        x = torch.randn(rows, hidden, generator=g, device=dev).to(dtype)
+        r = torch.randn(rows, hidden, generator=g, device=dev).to(dtype)
+        w = (1 + 0.1 * torch.randn(hidden, generator=g, device=dev)).to(dtype)
+        sid = torch.cuda.current_stream().cuda_stream
+        # rmsnorm(output, input, weight, eps, cuda_stream)
+        y = torch.empty_like(x)
+        ops.rmsnorm(y, x, w, 1e-6, sid)
+        y_e, _ = orc.add_rmsnorm(bits(x), None, bits(w), 1e-6, is_bf16)
+        np.testing.assert_allclose(y.float().cpu().numpy(), orc.from_bits(y_e, is_bf16), rtol=tol, atol=tol)
+        # fused_add_rmsnorm(input, residual, weight, eps, cuda_stream): both updated in place
+        x2, r2 = x.clone(), r.clone()
+        ops.fused_add_rmsnorm(x2, r2, w, 1e-6, sid)
+        y_e, r_e = orc.add_rmsnorm(bits(x), bits(r), bits(w), 1e-6, is_bf16)
+        torch.cuda.synchronize()
+        assert np.array_equal(bits(r2), r_e)                                  # the stored residual is bit-exact
+        np.testing.assert_allclose(x2.float().cpu().numpy(), orc.from_bits(y_e, is_bf16), rtol=tol, atol=tol)
+        # silu_and_mul(output, input, cuda_stream)
+        gu = torch.randn(rows, 2 * 384, generator=g, device=dev).to(dtype)
+        act = torch.empty(rows, 384, device=dev, dtype=dtype)
+        ops.silu_and_mul(act, gu)
+        np.testing.assert_allclose(act.float().cpu().numpy(), orc.from_bits(orc.silu_and_mul(bits(gu), is_bf16), is_bf16), rtol=tol, atol=tol)
+        # fused_qk_rmsnorm(IO, q_gamma, k_gamma, eps, q_group_num, k_group_num, m, n, norm_size): in place, v heads untouched
+        Hq, Hkv, D = 4, 2, 128
+        qkv = torch.randn(rows, (Hq + 2 * Hkv) * D, generator=g, device=dev).to(dtype)
+        qg = (1 + 0.1 * torch.randn(D, generator=g, device=dev)).to(dtype)
+        kg = (1 + 0.1 * torch.randn(D, generator=g, device=dev)).to(dtype)
+        exp = orc.qk_rmsnorm(bits(qkv), bits(qg), bits(kg), Hq, Hkv, D, 1e-6, is_bf16=is_bf16)
+        ops.fused_qk_rmsnorm(qkv, qg, kg, 1e-6, Hq, Hkv, rows, qkv.shape[1], D)
+        np.testing.assert_allclose(qkv.float().cpu().numpy(), orc.from_bits(exp, is_bf16), rtol=tol, atol=tol)
+        # embedding(output, input, weight)
+        table = torch.randn(50, 256, generator=g, device=dev).to(dtype)
+        ids = torch.tensor([3, 49, 0, 3], dtype=torch.int32, device=dev)
+        out = torch.empty(4, 256, device=dev, dtype=dtype)
+        ops.embedding(out, ids, table)
+        assert torch.equal(out, table[ids.long()])
+    with pytest.raises(RuntimeError):
+        ops.fused_qk_rmsnorm(qkv, qg, kg, 1e-6, Hq, Hkv, rows, qkv.shape[1], 64)   # n != (q + 2k) * norm_size
+
+
 @pytest.mark.gpu
 def test_pybind_attn_and_linear_ops_match_oracle():
     from oracle import oracle as orc
