@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import dataclasses
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -82,16 +83,14 @@ class DecodeStep:
         self.fuse_ar_norm = fuse_ar_norm
         # row-parallel GEMM + reduce-scatter in one kernel (b200_wo_gemm_rs), then gather + residual + norm (b200_peer_gather_norm):
         # only with the peer communicator and the fused all-reduce+norm; B200_FUSE_GEMM_RS=0 turns it off (A/B runs)
-        import os as _os
         if fuse_gemm_rs is None:
-            fuse_gemm_rs = _os.environ.get("B200_FUSE_GEMM_RS", "1") == "1"
+            fuse_gemm_rs = os.environ.get("B200_FUSE_GEMM_RS", "1") == "1"
         self.fuse_gemm_rs = (bool(fuse_gemm_rs) and fuse_ar_norm and tp_size > 1 and hasattr(comm, "gemm_rs")
                              and comm.gemm_rs_supported(batch, cfg.hidden))
         # RoPE + K/V append inside the attention kernel (b200_paged_decode_attn_rope): bit-identical, one launch less per layer,
         # but measured 0.4 % SLOWER at the headline config (same box A/B, profiles/r02_fuse_rope_ab.txt): under PDL the stand-alone
         # rope kernel hides behind its neighbours while the fused prologue sits on the attention kernel's critical path.
         # Default off; B200_FUSE_ROPE=1 or fuse_rope=True turns it on.
-        import os
         if fuse_rope is None:
             fuse_rope = os.environ.get("B200_FUSE_ROPE", "0") == "1"
         self.fuse_rope = bool(fuse_rope) and cfg.head_dim == 128
